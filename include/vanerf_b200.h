@@ -1,0 +1,168 @@
+/* libvanerf_b200.so — C ABI of the B200-native VANeRF novel-view render path.
+ *
+ * The reference (XuanHuang0/VANeRF) has no FFI / operator interface: its hot path is Python methods over torch.
+ * Each entry point below replaces the body of the reference function(s) cited next to it; the Python class
+ * `vanerf_b200.model.VANeRF` keeps the reference's call surface (src/model.py:748,1027,1103,1425,1465,1497) and
+ * binds these symbols with ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; no torch types cross the boundary.
+ *   - "dev" pointers are device pointers owned by the caller (e.g. the PyTorch caching allocator), "host" pointers
+ *     are host memory read synchronously during the call.
+ *   - every call enqueues its work on `stream` (a cudaStream_t passed as void*) and returns without synchronising;
+ *     the context owns only packed weights, per-frame acceleration structures and scratch.
+ *   - return value: 0 on success, a negative vanerf_status otherwise; no exceptions cross the ABI.
+ *   - one vanerf_ctx per device per process; calls on a context are ordered by the stream.
+ *   - sample index is the fastest dimension of every (ray, sample) array, as in the reference
+ *     (eval_pts.view(B,-1,3), src/model.py:1234-1235).
+ */
+#ifndef VANERF_B200_H
+#define VANERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VANERF_MAX_VIEWS 4
+#define VANERF_N_KPT 42          /* configs/vanerf.json: sp_args.n_kpt */
+#define VANERF_N_VERT 1558       /* 2 x (778 MANO + 1 seal vertex), src/networks.py:25 */
+#define VANERF_RAY_STRIDE 8      /* floats per ray record: dir.xyz, near, far, hit, pad, pad */
+
+typedef enum {
+    VANERF_OK = 0,
+    VANERF_ERR_INVALID = -1,     /* bad argument (NULL pointer, size out of range) */
+    VANERF_ERR_CUDA = -2,        /* CUDA runtime error (see vanerf_last_error) */
+    VANERF_ERR_STATE = -3,       /* call order violated (weights / frame not loaded) */
+    VANERF_ERR_UNSUPPORTED = -4  /* configuration outside the compiled limits */
+} vanerf_status;
+
+typedef enum { VANERF_FP32 = 0, VANERF_BF16 = 1 } vanerf_precision;
+
+typedef struct vanerf_ctx vanerf_ctx;
+
+/* One (out,in) row-major fp32 matrix with optional bias, host memory.  Weight-norm is already folded
+ * (W = g * v / ||v||, src/utils.py:670-685); Conv1d(k=1) weights have their trailing axis dropped. */
+typedef struct {
+    const float* w;
+    const float* b;              /* NULL = no bias */
+    int32_t out_dim, in_dim;
+} vanerf_linear;
+
+/* Hot-path parameters, host pointers. */
+typedef struct {
+    vanerf_linear geo_at[2], geo_f[2];      /* GeoVisFusion.fconv_at / fconv_ated   (src/networks.py:47-58)  */
+    vanerf_linear geo8_at[2], geo8_f[2];    /* GeoVisFusion.fconv_at1 / fconv_ated1 (src/networks.py:60-71)  */
+    vanerf_linear mlp[4];                   /* MLPUNet layers1 358-128-128-(136)120-64 (src/utils.py:822-852) */
+    vanerf_linear post[3];                  /* MLP layers2 128-64-64-2              (src/utils.py:687-719)   */
+    vanerf_linear compress;                 /* ibr_compress_gfeat 128-24            (src/model.py:633,921)   */
+    vanerf_linear tex_at[2], tex_f[2];      /* TexVisFusion.fconv_at / fconv        (src/networks.py:224-235) */
+    vanerf_linear ray[2], base[2], vis1[2], vis2[2], outl[3];   /* IBRRenderingHead (src/model.py:1578-1591) */
+    float ani_al;                           /* IBRRenderingHead.ani_al */
+    float sigmoid_beta;                     /* VANeRF.sigmoid_beta (clamped to >= 2e-3 by the library, model.py:880) */
+} vanerf_weights;
+
+/* Per-frame inputs: source cameras, source-view maps, two-hand mesh (reference layouts, fp32, NCHW). */
+typedef struct {
+    int32_t n_views, height, width;         /* source views V and source image size */
+    float znear, zfar;                      /* cam_in["znear"/"zfar"] */
+    float z_range;                          /* (float)(zfar - znear) evaluated in double, like the reference's python floats */
+    const float* KRT;                       /* host (V,4,4)  cam_in["KRT"]                     src/model.py:312   */
+    const float* extrin;                    /* host (V,4,4)  sp_data["extrin"]                 src/model.py:306   */
+    const float* src_cam_pos;               /* host (V,3)    inverse(KRT)[:, :3, 3]            src/model.py:937   */
+    const float* kpt3d;                     /* host (42,3)   sp_data["kpt3d"]                                     */
+    const float* verts;                     /* host (n_verts,3) targets["vert_world"]                             */
+    const int32_t* faces;                   /* host (n_faces,3) targets["face_world"]                             */
+    int32_t n_verts, n_faces;
+    const float* img;                       /* dev (V,3,H,W)                                                     */
+    const uint8_t* fg_mask;                 /* dev (V,H,W) 0/1   src_foreground_mask                              */
+    const float* feat_geo0; int32_t g0_h, g0_w;   /* dev (V,64,h,w) geo encoder level 0  src/networks.py:76      */
+    const float* feat_geo1; int32_t g1_h, g1_w;   /* dev (V,8,h,w)  geo encoder level 1  src/networks.py:77      */
+    const float* feat_tex;  int32_t t_h, t_w;     /* dev (V,8,h,w)  tex encoder          src/networks.py:78      */
+    const float* vert_gfeat;                /* dev (V,n_verts,18) TexVisFusion global feature (fconv_gt output,
+                                               src/networks.py:273-279), produced per frame by torch */
+} vanerf_frame;
+
+/* Target camera of one render (per-frame 3x3 matrices come from the same torch calls as the reference). */
+typedef struct {
+    float inv_K[9];      /* inverse(K[:3,:3]).T, row-major: d_cam = [x,y,1] @ inv_K      src/model.py:1208 */
+    float R[9];          /* RT[:3,:3] row-major: d_world = d_cam @ R                     src/model.py:1212 */
+    float cam_pos[3];    /* -(t^T R)                                                     src/model.py:1213 */
+    float znear, zfar;   /* frustum distances before the box clip                        src/model.py:1137 */
+    float bounds[6];     /* config["bounds"] (2,3): min xyz, max xyz (offset +-0.01 applied inside) :1216 */
+} vanerf_target;
+
+int  vanerf_ctx_create(vanerf_ctx** out, int device);
+void vanerf_ctx_destroy(vanerf_ctx* ctx);
+const char* vanerf_status_str(int status);
+const char* vanerf_last_error(const vanerf_ctx* ctx);
+int  vanerf_sm_count(const vanerf_ctx* ctx);
+
+/* Packs (transposes, pads, bf16-converts) the parameters into the context.  Replaces module construction +
+ * load_state_dict for the hot path (src/model.py:134-138, :605-667). */
+int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream);
+
+/* Per-frame setup: NHWC repack of the maps, vertex projection + per-view vertex visibility raster
+ * (src/model.py:1244-1255, mesh_util.py:284-318,484-489), visibility-premultiplied vertex feature tables
+ * (src/networks.py:83,96,270-279), camera-space keypoints (src/spatial.py:74-84), triangle / vertex BVHs.
+ * vert_vis_out: optional dev (V,n_verts) fp32 copy of the visibility table. */
+int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_out, void* stream);
+
+/* Ray generation, box clip, coarse depths (src/model.py:1190-1238, :1497-1570).
+ * pix_xy dev (R,2) int32 target pixels; ztab dev (S) = linspace(0,1,S); rays dev (R,8) out; z dev (R,S) out. */
+int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t n_rays,
+                       const float* ztab, int32_t n_samples, float* rays, float* z, void* stream);
+
+/* Signed distance to the mesh, closest face, nearest vertex, per-view sample visibility
+ * (mesh_util.py:498-524 = kaolin point_to_mesh_distance + check_sign; networks.py:28 = pytorch3d knn_points).
+ * Outputs dev: pts (N,3) sample positions, sdf (N), face (N), nn_vert (N), qvis (V,N).  Any output may be NULL
+ * except sdf/nn_vert/qvis when followed by vanerf_shade. */
+int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z,
+                      int32_t n_rays, int32_t n_samples, float* pts, float* sdf, int32_t* face,
+                      int32_t* nn_vert, uint8_t* qvis, void* stream);
+
+/* VANeRF.query + eval_func for N = n_rays*n_samples points (src/model.py:748-957, :1140-1160):
+ * projection, masks, pix_weight, feature gather, SpatialEncoder, GeoVisFusion, MLPUNetFusion, TexVisFusion,
+ * IBRRenderingHead.  rgba dev (N,5) = [valid*relu(o1), valid*o0 + (1-valid)*0.001, r, g, b]; valid dev (N) 0/1.
+ * raw_out: optional dev (N,5) = VANeRF.query's own output [o0,o1,r,g,b]. */
+int vanerf_shade(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* rays, const float* z,
+                 int32_t n_rays, int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis,
+                 float* rgba, uint8_t* valid, float* raw_out, void* stream);
+
+/* VANeRF.rgba2out (src/model.py:1465-1494), warp per ray.  mesh_sdf dev (R,S) is the signed mesh distance.
+ * out dev: color (R,3), depth (R), alpha (R), sdf_out (R), contrib (R,S); any may be NULL. */
+int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t n_rays,
+                     int32_t n_samples, float* color, float* depth, float* alpha, float* sdf_out, float* contrib,
+                     void* stream);
+
+/* VANeRF.importance_sample + merge sort (src/model.py:1301-1307, :1425-1462).  u dev (n_fine) shared by all rays
+ * (linspace(0,1,n_fine) for uniform=True) or (R,n_fine) when u_per_ray != 0.  z_out dev (R, S + n_fine) sorted. */
+int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int32_t n_rays, int32_t n_samples,
+                      const float* u, int32_t n_fine, int32_t u_per_ray, float* z_fine_only, float* z_out,
+                      void* stream);
+
+/* One call for VANeRF.batch_render_pifu_nerf's ray batch (src/model.py:1103-1422, inference branch):
+ * rays -> coarse pass -> composite -> importance -> fine pass -> composite, chunked internally.
+ * ztab dev (n_coarse) = linspace(0,1,n_coarse), utab dev (n_fine) = linspace(0,1,n_fine) (uniform=True).
+ * out_coarse / out_fine dev (R,8): r,g,b, depth, alpha, sdf, 0, 0 (out_fine may be NULL when fine == 0). */
+int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const int32_t* pix_xy,
+                       int32_t n_rays, int32_t n_coarse, int32_t n_fine, int32_t fine, const float* ztab,
+                       const float* utab, float* out_coarse, float* out_fine, void* stream);
+
+/* Scratch the context needs for vanerf_render_rays / vanerf_shade at the given sizes (bytes). */
+size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t n_rays, int32_t n_samples);
+
+/* Test hook: vanerf_shade (fp32) that also returns MLPUNetFusion's pooled latent (N,128). */
+int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t n_rays,
+                       int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba,
+                       uint8_t* valid, float* raw_out, float* latent, void* stream);
+
+/* Number of kernels launched by this context since creation (for bench.py's gpu_launches). */
+int64_t vanerf_launch_count(const vanerf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VANERF_B200_H */

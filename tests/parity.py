@@ -1,0 +1,151 @@
+"""Stage-by-stage parity checks of the kernel path against the oracle, shared by the GPU tests (CUDA library through
+the C ABI) and the CPU-side logic tests (host-emulation build of the same kernel sources).
+
+Bars (BASELINE.json north_star): sample depths / positions, indices and masks bit-exact; colour / density within
+1e-3 max-abs for the fp32 path, 1e-2 for the bf16-MLP path.  Stage checks feed each kernel the ORACLE's upstream
+tensors where a float-path difference would otherwise be amplified (importance sampling, fine pass).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import oracle_torch as OT
+from vanerf_b200 import _lib as L
+from vanerf_b200 import synthetic, weights
+from vanerf_b200.renderer import Renderer
+
+TOL_FP32 = 1e-3
+TOL_BF16 = 1e-2
+
+
+def lattice_pixels(H, W, npix):
+    """Config-A style lattice of target pixels spread over the image."""
+    ii, jj = np.meshgrid(np.arange(npix), np.arange(npix), indexing="ij")
+    xs = (W // (2 * npix) + (W // npix) * ii).ravel()
+    ys = (H // (2 * npix) + (H // npix) * jj).ravel()
+    return np.stack([xs, ys], 1).astype(np.int64)
+
+
+def build_case(H, W, V, mode="stress", layout="narrow", mask="silhouette", frame=0):
+    sc = synthetic.make_scene(H, W, V, layout=layout, mask=mask, frame=frame)
+    inp = synthetic.to_torch(sc)
+    sd = weights.init_state_dict(H, W, mode=mode)
+    return sc, inp, sd
+
+
+def make_renderer(inp, sd, device, lib=None):
+    r = Renderer(device, lib)
+    r.load_state_dict(sd)
+    dev = r.device
+    mv = lambda t: t.to(dev)
+    vert_vis = r.set_frame(mv(inp["img"]), inp["cam_in"], inp["targets"], inp["sp_data"], [mv(t) for t in inp["feat_geo"]],
+                           mv(inp["feat_tex"]), mv(inp["src_foreground_mask"]))
+    return r, vert_vis
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_exact(name, got, ref):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, f"{name}: shape {got.shape} vs {ref.shape}"
+    if got.dtype.kind == "f":
+        bad = got.view(np.uint32) != ref.astype(np.float32).view(np.uint32)
+    else:
+        bad = got != ref
+    assert not bad.any(), f"{name}: {int(bad.sum())}/{bad.size} elements differ (bit-exact required)"
+
+
+def assert_close(name, got, ref, tol):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, f"{name}: shape {got.shape} vs {ref.shape}"
+    assert np.isfinite(got).all(), f"{name}: non-finite values"
+    err = np.abs(got - ref).max()
+    assert err <= tol, f"{name}: max-abs error {err:.3e} > {tol:.1e} (|ref| max {np.abs(ref).max():.3e})"
+    return err
+
+
+def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, S_f=64, report=None):
+    """Runs every stage on `r` and compares with the oracle.  Returns a dict of max-abs errors."""
+    tol = TOL_FP32 if precision == L.FP32 else TOL_BF16
+    orc = OT.Oracle(sd, inp)
+    ot = {}
+    oo = orc.render(fine=True, pixels=pixels, S_c=S_c, S_f=S_f, taps=ot)
+    errs = {}
+    # ---- per-frame visibility (bit-exact)
+    assert_exact("vert_vis", _np(vert_vis), orc.frame["vert_vis"])
+    tar = r.make_target(inp["cam_tar"], inp["bounds"])
+    pix = torch.from_numpy(pixels)
+    # ---- rays + coarse depths (bit-exact)
+    rays, z = r.sample_rays(tar, pix, S_c)
+    rn = _np(rays)
+    assert_exact("ray dirs", rn[:, :3], ot["rays"]["dirs"])
+    assert_exact("ray near", rn[:, 3], ot["rays"]["znear"])
+    assert_exact("ray far", rn[:, 4], ot["rays"]["zfar"])
+    assert_exact("ray hit", rn[:, 5] > 0, ot["rays"]["hit"])
+    assert_exact("z coarse", _np(z), ot["z"])
+    # ---- geometry (bit-exact)
+    geo = r.geom_query(tar, rays, z)
+    assert_exact("sample positions", _np(geo["pts"]), ot["pts"])
+    assert_exact("closest face", _np(geo["face"]).astype(np.int64), ot["geo"]["face"])
+    assert_exact("nearest vertex", _np(geo["nn"]).astype(np.int64), ot["geo"]["nn"])
+    assert_exact("query_vis", _np(geo["qvis"]) > 0, ot["geo"]["qvis"])
+    assert_exact("mesh sdf", _np(geo["sdf"]), ot["geo"]["sdf"])
+    # ---- shading, coarse
+    if precision == L.FP32:
+        rgba, valid, raw, lat = r.shade(tar, rays, z, geo, want_latent=True)
+        errs["latent"] = assert_close("MLPUNetFusion latent", _np(lat), ot["query"]["latent"], tol)
+    else:
+        rgba, valid, raw = r.shade(tar, rays, z, geo, precision=precision)
+    assert_exact("valid", _np(valid) > 0, ot["valid"])
+    errs["query_out"] = assert_close("VANeRF.query out", _np(raw), np.concatenate([ot["query"]["o"], ot["query"]["rgb"]], 1), tol)
+    errs["rgba"] = assert_close("rgba", _np(rgba), ot["rgba"], tol)
+    # ---- compositing given the oracle's rgba (isolates the kernel), then end to end
+    dev = r.device
+    comp_o = r.composite(torch.from_numpy(ot["rgba"]).to(dev), z, geo["sdf"].view(z.shape))
+    ref_c = orc.rgba2out(ot["rgba"].reshape(z.shape[0], S_c, 5), ot["z"], ot["geo"]["sdf"].reshape(z.shape))
+    errs["composite_kernel"] = max(assert_close("composite colour", _np(comp_o["color"]), ref_c["color"], 1e-5),
+                                   assert_close("composite contrib", _np(comp_o["contrib"]), ref_c["contrib"], 1e-5),
+                                   assert_close("composite depth", _np(comp_o["depth"]), ref_c["depth"], 1e-5),
+                                   assert_close("composite alpha", _np(comp_o["alpha"]), ref_c["alpha"], 1e-5),
+                                   assert_close("composite sdf", _np(comp_o["sdf"]), ref_c["sdf"], 1e-5))
+    comp = r.composite(rgba, z, geo["sdf"].view(z.shape))
+    errs["tex_fg"] = assert_close("tex_fg", _np(comp["color"]), oo["tex_fg"], tol)
+    errs["depth"] = assert_close("depth", _np(comp["depth"]), oo["depth"], tol)
+    errs["alpha"] = assert_close("alpha", _np(comp["alpha"]), oo["alpha"], tol)
+    # ---- importance sampling + merge given the oracle's contrib: bit-exact fine depths
+    zf, zall = r.importance(torch.from_numpy(ot["contrib"]).to(dev), torch.from_numpy(ot["z"]).to(dev), S_f)
+    assert_exact("z_fine", _np(zf), ot["z_fine_only"])
+    assert_exact("z merged", _np(zall), ot["z_fine"])
+    # ---- fine pass on the oracle's fine depths
+    z2 = torch.from_numpy(ot["z_fine"]).to(dev)
+    geo2 = r.geom_query(tar, rays, z2)
+    assert_exact("fine positions", _np(geo2["pts"]), ot["pts_fine"])
+    assert_exact("fine closest face", _np(geo2["face"]).astype(np.int64), ot["geo_fine"]["face"])
+    assert_exact("fine query_vis", _np(geo2["qvis"]) > 0, ot["geo_fine"]["qvis"])
+    rgba2, valid2, raw2 = r.shade(tar, rays, z2, geo2, precision=precision)
+    assert_exact("fine valid", _np(valid2) > 0, ot["valid_fine"])
+    errs["rgba_fine"] = assert_close("rgba fine", _np(rgba2), ot["rgba_fine"], tol)
+    comp2 = r.composite(rgba2, z2, geo2["sdf"].view(z2.shape))
+    errs["tex_fg_fine"] = assert_close("tex_fg_fine", _np(comp2["color"]), oo["tex_fg_fine"], tol)
+    errs["sdf_fine"] = assert_close("sdf fine", _np(comp2["sdf"]), oo["sdf"], tol)
+    if report is not None:
+        report.update(errs)
+    return errs, oo, ot
+
+
+def check_render_rays(r: Renderer, inp, oo, pixels, precision=L.FP32, tol_fine=None):
+    """The fused entry point (coarse + importance + fine in one call) against the oracle's end-to-end render."""
+    tol = TOL_FP32 if precision == L.FP32 else TOL_BF16
+    tar = r.make_target(inp["cam_tar"], inp["bounds"])
+    oc, of = r.render_rays(tar, torch.from_numpy(pixels), 64, 64, True, precision)
+    oc, of = _np(oc), _np(of)
+    e = {"rr_tex_fg": assert_close("render_rays tex_fg", oc[:, :3], oo["tex_fg"], tol),
+         "rr_depth": assert_close("render_rays depth", oc[:, 3], oo["depth"], tol),
+         "rr_alpha": assert_close("render_rays alpha", oc[:, 4], oo["alpha"], tol)}
+    # the fine pass re-samples from a cdf: its depths amplify fp rounding of contrib (reference vs its own CPU
+    # restatement already differ by ~1e-3 on stress weights), hence the separate tolerance
+    e["rr_tex_fg_fine"] = assert_close("render_rays tex_fg_fine", of[:, :3], oo["tex_fg_fine"], tol_fine or tol)
+    return e

@@ -2,21 +2,20 @@
 //
 // There is no GPU in the build container, so the SIMT kernels of this package can also be compiled as plain
 // C++ (g++ -DVANERF_HOST_EMUL -ffp-contract=off) into tests/_emul/libvanerf_emul.so, where a thread block is a
-// group of OS threads, __syncthreads() is a barrier and warp shuffles go through a per-warp exchange buffer.
+// group of fibers, __syncthreads() is a barrier and warp shuffles go through a per-warp exchange buffer.
 // Only tests/ load that library, to check kernel logic against the oracle before GPU time is spent.  The product
 // (vanerf_b200/_lib.py) loads the nvcc-built libvanerf_b200.so only and raises if it is missing: this header is
 // never part of that build.  tcgen05 / TMA kernels are not emulated.
 #pragma once
 #ifdef VANERF_HOST_EMUL
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
-#include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
-#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -44,22 +43,17 @@ static inline float3 make_float3(float x, float y, float z) { return float3{x, y
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 
+using std::max;
+using std::min;
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 #define cudaSuccess 0
 
 namespace emul {
-struct Barrier {
-    std::mutex m;
-    std::condition_variable cv;
+struct Barrier {                  // members of a block are fibers on one OS thread: no locking needed
     int count = 0, gen = 0, n = 0;
     void init(int n_) { n = n_; count = 0; gen = 0; }
-    void wait() {
-        std::unique_lock<std::mutex> lk(m);
-        int g = gen;
-        if (++count == n) { gen++; count = 0; cv.notify_all(); }
-        else cv.wait(lk, [&] { return g != gen; });
-    }
+    void wait();
 };
 struct Block {
     Barrier bar;
@@ -79,8 +73,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 #define gridDim (emul::g_gridDim)
 #define warpSize 32
 
-// __shared__ variables: blocks run one after another, so a function-level static is per-block storage.
-#define __shared__ static
+// __shared__ variables: one block at a time per OS thread, so thread-local statics are per-block storage.
+#define __shared__ static thread_local
 #define EMUL_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emul::t_block->dyn_smem)
 
 static inline void __syncthreads() { emul::t_block->bar.wait(); }
@@ -126,12 +120,7 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
-static inline float __expf(float a) { return expf(a); }
-static inline float __logf(float a) { return logf(a); }
-static inline float __sinf(float a) { return sinf(a); }
-static inline float __cosf(float a) { return cosf(a); }
 static inline float __fdividef(float a, float b) { return a / b; }
-static inline void sincosf_(float a, float* s, float* c) { *s = sinf(a); *c = cosf(a); }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
@@ -150,6 +139,21 @@ static inline unsigned long long atomicMin(unsigned long long* a, unsigned long 
 static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicOr(unsigned* a, unsigned v) { return __atomic_fetch_or(a, v, __ATOMIC_RELAXED); }
 static inline int atomicExch(int* a, int v) { return __atomic_exchange_n(a, v, __ATOMIC_RELAXED); }
+
+// ---- just enough of the CUDA runtime API for api.cu (host memory stands in for device memory)
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return 0; }
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 #define VANERF_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emul::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })

@@ -1,0 +1,413 @@
+// libvanerf_b200.so: context, weight packing, per-frame setup and kernel launchers behind the C ABI of
+// include/vanerf_b200.h.  Single translation unit: the kernels live in the .cuh files included below.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "bvh.h"
+#include "rays.cuh"
+#include "geom.cuh"
+#include "frame.cuh"
+#include "gather.cuh"
+#include "mlp_simt.cuh"
+#include "composite.cuh"
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct vanerf_ctx {
+    int device = 0, sm_count = 148;
+    int64_t launches = 0;
+    char err[512] = {0};
+    // weights
+    DevBuf wblob, netdev, tcw;
+    NetDev h_net;
+    bool have_weights = false;
+    // frame
+    FrameDev fr;
+    bool have_frame = false;
+    DevBuf geo0, geo1, tex, imgm, T64, T8, Ttex, vis, verts, faces, tri_nodes, tri_prims, vtx_nodes, vtx_prims,
+        kpt_cam, xyz_ndc, xy11, zbuf;
+    // scratch
+    DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
+};
+
+#ifndef VANERF_HOST_EMUL
+// tensor-core (tcgen05) path, defined in mlp_tc.cuh (included at the end of this file)
+static int tc_pack_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream);
+static int tc_shade_chunk(vanerf_ctx* ctx, const float* rec, long long sample0, int n_chunk, float* rgba, float* raw_out,
+                          cudaStream_t stream);
+#endif
+
+static int ctx_fail(vanerf_ctx* ctx, cudaError_t e, const char* what, int line) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "CUDA error %d (%s) at %s [vanerf_b200.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
+    return VANERF_ERR_CUDA;
+}
+static int ctx_invalid(vanerf_ctx* ctx, const char* msg) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "invalid argument: %s", msg);
+    return VANERF_ERR_INVALID;
+}
+
+static int ensure(vanerf_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+#define ENSURE(ctx, buf, bytes) do { int rc_ = ensure((ctx), (buf), (bytes)); if (rc_) return rc_; } while (0)
+#define CHECK_LAUNCH(ctx) do { (ctx)->launches++; CUDA_TRY((ctx), cudaGetLastError()); } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+extern "C" {
+
+int vanerf_ctx_create(vanerf_ctx** out, int device) {
+    if (!out) return VANERF_ERR_INVALID;
+    vanerf_ctx* c = new vanerf_ctx();
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
+    int sm = 0;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
+    c->sm_count = sm;
+    memset(&c->fr, 0, sizeof(c->fr));
+    memset(&c->h_net, 0, sizeof(c->h_net));
+    *out = c;
+    return VANERF_OK;
+}
+
+void vanerf_ctx_destroy(vanerf_ctx* c) {
+    if (!c) return;
+    DevBuf* all[] = {&c->wblob, &c->netdev, &c->tcw, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
+                     &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
+                     &c->xyz_ndc, &c->xy11, &c->zbuf, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
+                     &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab};
+    for (DevBuf* b : all) if (b->p) cudaFree(b->p);
+    delete c;
+}
+
+const char* vanerf_status_str(int s) {
+    switch (s) {
+        case VANERF_OK: return "ok";
+        case VANERF_ERR_INVALID: return "invalid argument";
+        case VANERF_ERR_CUDA: return "CUDA runtime error";
+        case VANERF_ERR_STATE: return "call order violated (load weights, then frame_setup, then render)";
+        case VANERF_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown status";
+    }
+}
+const char* vanerf_last_error(const vanerf_ctx* c) { return c ? c->err : "no context"; }
+int vanerf_sm_count(const vanerf_ctx* c) { return c ? c->sm_count : 0; }
+int64_t vanerf_launch_count(const vanerf_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ weights
+int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) {
+    if (!ctx || !w) return VANERF_ERR_INVALID;
+    const vanerf_linear* src[L_COUNT] = {
+        &w->geo_at[0], &w->geo_at[1], &w->geo_f[0], &w->geo_f[1], &w->geo8_at[0], &w->geo8_at[1], &w->geo8_f[0], &w->geo8_f[1],
+        &w->mlp[0], &w->mlp[1], &w->mlp[2], &w->mlp[3], &w->post[0], &w->post[1], &w->post[2], &w->compress,
+        &w->tex_at[0], &w->tex_at[1], &w->tex_f[0], &w->tex_f[1],
+        &w->ray[0], &w->ray[1], &w->base[0], &w->base[1], &w->vis1[0], &w->vis1[1], &w->vis2[0], &w->vis2[1],
+        &w->outl[0], &w->outl[1], &w->outl[2]};
+    static const int expect[L_COUNT][2] = {   // (out, in) of configs/vanerf.json
+        {10, 196}, {3, 10}, {64, 196}, {64, 64}, {10, 28}, {3, 10}, {8, 28}, {8, 8},
+        {128, 358}, {128, 128}, {120, 136}, {64, 120}, {64, 128}, {64, 64}, {2, 64}, {24, 128},
+        {96, 96}, {6, 96}, {96, 96}, {40, 96},
+        {16, 4}, {40, 16}, {64, 120}, {32, 64}, {32, 32}, {33, 32}, {32, 32}, {1, 32}, {16, 37}, {8, 16}, {1, 8}};
+    size_t total = 0;
+    std::vector<size_t> off_w(L_COUNT), off_b(L_COUNT);
+    for (int i = 0; i < L_COUNT; ++i) {
+        if (!src[i]->w) return ctx_invalid(ctx, "NULL weight matrix");
+        if (src[i]->out_dim != expect[i][0] || src[i]->in_dim != expect[i][1]) {
+            snprintf(ctx->err, sizeof(ctx->err), "layer %d: expected (%d,%d) got (%d,%d)", i, expect[i][0], expect[i][1], src[i]->out_dim, src[i]->in_dim);
+            return VANERF_ERR_UNSUPPORTED;
+        }
+        const int npad = (src[i]->out_dim + 7) & ~7;
+        off_w[i] = total; total += (size_t)src[i]->in_dim * npad;
+        off_b[i] = total; total += npad;
+        total = (total + 3) & ~(size_t)3;
+    }
+    std::vector<float> blob(total, 0.0f);
+    ENSURE(ctx, ctx->wblob, total * sizeof(float));
+    ENSURE(ctx, ctx->netdev, sizeof(NetDev));
+    for (int i = 0; i < L_COUNT; ++i) {
+        const int N = src[i]->out_dim, K = src[i]->in_dim, npad = (N + 7) & ~7;
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < K; ++k) blob[off_w[i] + (size_t)k * npad + n] = src[i]->w[(size_t)n * K + k];
+        if (src[i]->b) for (int n = 0; n < N; ++n) blob[off_b[i] + n] = src[i]->b[n];
+        LayerDev& L = ctx->h_net.layer[i];
+        L.wt = (const float*)ctx->wblob.p + off_w[i];
+        L.b = (const float*)ctx->wblob.p + off_b[i];
+        L.K = K; L.N = N; L.Npad = npad; L.pad_ = 0;
+    }
+    ctx->h_net.ani_al_abs = fabsf(w->ani_al);
+    ctx->h_net.beta = fmaxf(w->sigmoid_beta, 2e-3f);           // sdf_activation clamp (src/model.py:880)
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->wblob.p, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->netdev.p, &ctx->h_net, sizeof(NetDev), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // host staging buffers go out of scope
+#ifndef VANERF_HOST_EMUL
+    { int rc = tc_pack_weights(ctx, w, stream); if (rc) return rc; }
+#endif
+    ctx->have_weights = true;
+    return VANERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ frame
+int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_out, void* stream_) {
+    if (!ctx || !f) return VANERF_ERR_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int V = f->n_views, H = f->height, W = f->width, Nv = f->n_verts, F = f->n_faces;
+    if (V < 1 || V > MAXV) return ctx_invalid(ctx, "n_views out of range (1..4)");
+    if (Nv != 2 * NUM_V_HAND) return ctx_invalid(ctx, "mesh must have 1558 vertices (two sealed MANO hands)");
+    if (!f->KRT || !f->extrin || !f->src_cam_pos || !f->kpt3d || !f->verts || !f->faces || !f->img || !f->fg_mask ||
+        !f->feat_geo0 || !f->feat_geo1 || !f->feat_tex || !f->vert_gfeat)
+        return ctx_invalid(ctx, "NULL pointer in vanerf_frame");
+    FrameDev& fr = ctx->fr;
+    fr.V = V; fr.H = H; fr.W = W; fr.n_verts = Nv; fr.n_faces = F;
+    fr.znear = f->znear; fr.zfar = f->zfar; fr.z_range = f->z_range;
+    memcpy(fr.KRT, f->KRT, sizeof(float) * 16 * V);
+    memcpy(fr.extrin, f->extrin, sizeof(float) * 16 * V);
+    memcpy(fr.src_pos, f->src_cam_pos, sizeof(float) * 3 * V);
+    fr.g0h = f->g0_h; fr.g0w = f->g0_w; fr.g1h = f->g1_h; fr.g1w = f->g1_w; fr.th = f->t_h; fr.tw = f->t_w;
+
+    // keypoints in each source camera frame: kc = kpt3d @ R^T + t (src/spatial.py:84), exact-op order on the host
+    std::vector<float> kc((size_t)V * NKPT * 3);
+    for (int v = 0; v < V; ++v)
+        for (int k = 0; k < NKPT; ++k)
+            for (int j = 0; j < 3; ++j) {
+                const float* M = f->extrin + 16 * v;
+                const float* p = f->kpt3d + 3 * k;
+                volatile float a = p[0] * M[4 * j], b = p[1] * M[4 * j + 1], c = p[2] * M[4 * j + 2];
+                volatile float s = a + b;
+                volatile float t = s + c;
+                kc[((size_t)v * NKPT + k) * 3 + j] = t + M[4 * j + 3];
+            }
+    bvh::Tree tt, vt;
+    bvh::build_triangles(f->verts, f->faces, F, tt);
+    bvh::build_points(f->verts, Nv, vt);
+
+    const size_t g0n = (size_t)V * 64 * fr.g0h * fr.g0w, g1n = (size_t)V * 8 * fr.g1h * fr.g1w, txn = (size_t)V * 8 * fr.th * fr.tw;
+    ENSURE(ctx, ctx->geo0, g0n * 4); ENSURE(ctx, ctx->geo1, g1n * 4); ENSURE(ctx, ctx->tex, txn * 4);
+    ENSURE(ctx, ctx->imgm, (size_t)V * H * W * 16);
+    ENSURE(ctx, ctx->T64, (size_t)V * Nv * 64 * 4); ENSURE(ctx, ctx->T8, (size_t)V * Nv * 8 * 4); ENSURE(ctx, ctx->Ttex, (size_t)V * Nv * 32 * 4);
+    ENSURE(ctx, ctx->vis, (size_t)V * Nv * 4);
+    ENSURE(ctx, ctx->verts, (size_t)Nv * 12); ENSURE(ctx, ctx->faces, (size_t)F * 12);
+    ENSURE(ctx, ctx->tri_nodes, tt.nodes.size() * 4); ENSURE(ctx, ctx->tri_prims, tt.prims.size() * 4);
+    ENSURE(ctx, ctx->vtx_nodes, vt.nodes.size() * 4); ENSURE(ctx, ctx->vtx_prims, vt.prims.size() * 4);
+    ENSURE(ctx, ctx->kpt_cam, kc.size() * 4);
+    ENSURE(ctx, ctx->xyz_ndc, (size_t)V * Nv * 12); ENSURE(ctx, ctx->xy11, (size_t)V * Nv * 8);
+    ENSURE(ctx, ctx->zbuf, (size_t)V * RASTER_S * RASTER_S * 8);
+
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->verts.p, f->verts, (size_t)Nv * 12, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->faces.p, f->faces, (size_t)F * 12, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_nodes.p, tt.nodes.data(), tt.nodes.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_prims.p, tt.prims.data(), tt.prims.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_nodes.p, vt.nodes.data(), vt.nodes.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_prims.p, vt.prims.data(), vt.prims.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kpt_cam.p, kc.data(), kc.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));       // pageable host staging above goes out of scope
+
+    fr.geo0 = (const float*)ctx->geo0.p; fr.geo1 = (const float*)ctx->geo1.p; fr.tex = (const float*)ctx->tex.p;
+    fr.imgm = (const float*)ctx->imgm.p;
+    fr.T64 = (const float*)ctx->T64.p; fr.T8 = (const float*)ctx->T8.p; fr.Ttex = (const float*)ctx->Ttex.p;
+    fr.vis = (const float*)ctx->vis.p;
+    fr.verts = (const float*)ctx->verts.p; fr.faces = (const int*)ctx->faces.p;
+    fr.tri_nodes = (const float4*)ctx->tri_nodes.p; fr.tri_prims = (const int*)ctx->tri_prims.p;
+    fr.vtx_nodes = (const float4*)ctx->vtx_nodes.p; fr.vtx_prims = (const int*)ctx->vtx_prims.p;
+    fr.kpt_cam = (const float*)ctx->kpt_cam.p;
+
+    const int T = 256;
+    VANERF_LAUNCH(k_repack_nhwc, cdiv(g0n, T), T, 0, stream, f->feat_geo0, (float*)ctx->geo0.p, V, 64, fr.g0h, fr.g0w); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_repack_nhwc, cdiv(g1n, T), T, 0, stream, f->feat_geo1, (float*)ctx->geo1.p, V, 8, fr.g1h, fr.g1w); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_repack_nhwc, cdiv(txn, T), T, 0, stream, f->feat_tex, (float*)ctx->tex.p, V, 8, fr.th, fr.tw); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_repack_imgm, cdiv((long long)V * H * W, T), T, 0, stream, f->img, f->fg_mask, (float4*)ctx->imgm.p, V, H, W); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_project_verts, cdiv(V * Nv, T), T, 0, stream, fr, (float*)ctx->xyz_ndc.p, (float*)ctx->xy11.p); CHECK_LAUNCH(ctx);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->zbuf.p, 0xff, (size_t)V * RASTER_S * RASTER_S * 8, stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->vis.p, 0, (size_t)V * Nv * 4, stream));
+    VANERF_LAUNCH(k_raster_faces, cdiv(V * F, 128), 128, 0, stream, fr, (const float*)ctx->xyz_ndc.p, (unsigned long long*)ctx->zbuf.p); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_resolve_vis, cdiv(V * RASTER_S * RASTER_S, T), T, 0, stream, fr, (const unsigned long long*)ctx->zbuf.p, (float*)ctx->vis.p); CHECK_LAUNCH(ctx);
+    VANERF_LAUNCH(k_vertex_tables, cdiv((long long)V * Nv * 104, T), T, 0, stream, fr, (const float*)ctx->xy11.p, f->vert_gfeat,
+                  (float*)ctx->T64.p, (float*)ctx->T8.p, (float*)ctx->Ttex.p); CHECK_LAUNCH(ctx);
+    if (vert_vis_out)
+        CUDA_TRY(ctx, cudaMemcpyAsync(vert_vis_out, ctx->vis.p, (size_t)V * Nv * 4, cudaMemcpyDeviceToDevice, stream));
+    ctx->have_frame = true;
+    return VANERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-ray stages
+static TargetDev make_target(const vanerf_target* t) {
+    TargetDev d;
+    memcpy(d.inv_K, t->inv_K, sizeof(d.inv_K));
+    memcpy(d.R, t->R, sizeof(d.R));
+    memcpy(d.cam_pos, t->cam_pos, sizeof(d.cam_pos));
+    d.znear = t->znear; d.zfar = t->zfar;
+    for (int c = 0; c < 3; ++c) {          // bounds + boffset (-0.01, +0.01), fp32 adds (src/model.py:1518)
+        volatile float lo = t->bounds[c] + (-0.01f), hi = t->bounds[3 + c] + 0.01f;
+        d.bmin[c] = lo; d.bmax[c] = hi;
+    }
+    return d;
+}
+
+int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t R, const float* ztab,
+                       int32_t S, float* rays, float* z, void* stream) {
+    if (!ctx || !tar || !pix_xy || !ztab || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_sample_rays");
+    VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ztab, S, rays, z);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
+                      float* pts, float* sdf, int32_t* face, int32_t* nn_vert, uint8_t* qvis, void* stream) {
+    if (!ctx || !tar || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_geom_query");
+    if (!ctx->have_frame) return VANERF_ERR_STATE;
+    const long long N = (long long)R * S;
+    VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, R, S, pts, sdf, face, nn_vert, qvis);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+#define SHADE_CHUNK 65536      // samples per gather/MLP round; records: chunk * V * 1232 B
+
+static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const float* rays, const float* z, int R, int S,
+                      const float* sdf, const int* nn, const unsigned char* qvis, float* rgba, unsigned char* valid,
+                      float* raw_out, float* dbg_latent, cudaStream_t stream) {
+    const long long N = (long long)R * S;
+    const int V = ctx->fr.V;
+    const int chunk = (int)(N < SHADE_CHUNK ? N : SHADE_CHUNK);
+    ENSURE(ctx, ctx->rec, (size_t)chunk * V * REC_STRIDE * 4);
+    const size_t smem = mlp_simt_smem_floats(V) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        attr_set = true;
+    }
+    for (long long s0 = 0; s0 < N; s0 += chunk) {
+        const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
+        const int gblocks = min(cdiv(nc, GATHER_THREADS / 16), ctx->sm_count * 8);
+        VANERF_LAUNCH(k_gather, gblocks, GATHER_THREADS, 0, stream, ctx->fr, td, rays, z, S, s0, nc, N, sdf, nn, qvis,
+                      (float*)ctx->rec.p, valid);
+        CHECK_LAUNCH(ctx);
+#ifndef VANERF_HOST_EMUL
+        if (precision == VANERF_BF16) {
+            int rc = tc_shade_chunk(ctx, (const float*)ctx->rec.p, s0, nc, rgba, raw_out, stream);
+            if (rc) return rc;
+            continue;
+        }
+#endif
+        const int mblocks = min(cdiv(nc, TS), ctx->sm_count);
+        VANERF_LAUNCH(k_mlp_simt, mblocks, MLP_THREADS, smem, stream, (const NetDev*)ctx->netdev.p, ctx->fr.kpt_cam, V,
+                      (const float*)ctx->rec.p, s0, nc, rgba, raw_out, dbg_latent);
+        CHECK_LAUNCH(ctx);
+    }
+    return VANERF_OK;
+}
+
+int vanerf_shade(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* rays, const float* z, int32_t R,
+                 int32_t S, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
+                 float* raw_out, void* stream) {
+    if (!ctx || !tar || !rays || !z || !sdf || !nn_vert || !qvis || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_shade");
+    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (precision != VANERF_FP32 && precision != VANERF_BF16) return ctx_invalid(ctx, "precision");
+    return shade_impl(ctx, precision, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, nullptr,
+                      (cudaStream_t)stream);
+}
+
+// test hook: like vanerf_shade (fp32) but also returns the pooled 128-wide latent of MLPUNetFusion (N,128)
+int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
+                       const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
+                       float* raw_out, float* latent, void* stream) {
+    if (!ctx || !tar) return VANERF_ERR_INVALID;
+    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    return shade_impl(ctx, VANERF_FP32, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
+                      (cudaStream_t)stream);
+}
+
+int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t R, int32_t S,
+                     float* color, float* depth, float* alpha, float* sdf_out, float* contrib, void* stream) {
+    if (!ctx || !rgba || !z || !mesh_sdf || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_composite");
+    if (S > 32 * COMP_MAX_PER_LANE) return VANERF_ERR_UNSUPPORTED;
+    if (!ctx->have_weights) return VANERF_ERR_STATE;
+    const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    VANERF_LAUNCH(k_composite, blocks, COMP_WARPS * 32, 0, stream, rgba, z, mesh_sdf, R, S, ctx->h_net.beta, color, depth, alpha,
+                  sdf_out, contrib);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int32_t R, int32_t S, const float* u,
+                      int32_t nf, int32_t u_per_ray, float* z_fine_only, float* z_out, void* stream) {
+    if (!ctx || !contrib || !z || !u || !z_out || R <= 0 || S < 3 || nf <= 0) return ctx_invalid(ctx, "vanerf_importance");
+    const size_t smem = (size_t)COMP_WARPS * (2 * (S - 1) + S + nf) * sizeof(float);
+    if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
+    const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, R, S, u, nf, u_per_ray, z_fine_only, z_out);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t R, int32_t S) {
+    const int V = ctx && ctx->have_frame ? ctx->fr.V : MAXV;
+    const size_t N = (size_t)R * S;
+    return N * (4 + 4 + 4 + V + 20 + 4 + 1) + (size_t)R * 32 + (size_t)SHADE_CHUNK * V * REC_STRIDE * 4;
+}
+
+#define RENDER_RAY_CHUNK 8192
+
+int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const int32_t* pix_xy, int32_t R,
+                       int32_t Sc, int32_t Sf, int32_t fine, const float* ztab, const float* utab, float* out_coarse,
+                       float* out_fine, void* stream_) {
+    if (!ctx || !tar || !pix_xy || !ztab || !out_coarse || R <= 0 || Sc < 3) return ctx_invalid(ctx, "vanerf_render_rays");
+    if (fine && (!utab || !out_fine || Sf <= 0)) return ctx_invalid(ctx, "vanerf_render_rays: fine pass needs utab/out_fine");
+    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const TargetDev td = make_target(tar);
+    const int V = ctx->fr.V;
+    const int S2 = fine ? Sc + Sf : Sc;
+    const int RC = R < RENDER_RAY_CHUNK ? R : RENDER_RAY_CHUNK;
+    const size_t Nmax = (size_t)RC * S2;
+    ENSURE(ctx, ctx->s_rays, (size_t)RC * VANERF_RAY_STRIDE * 4);
+    ENSURE(ctx, ctx->s_z, (size_t)RC * Sc * 4);
+    ENSURE(ctx, ctx->s_z2, Nmax * 4);
+    ENSURE(ctx, ctx->s_sdf, Nmax * 4);
+    ENSURE(ctx, ctx->s_nn, Nmax * 4);
+    ENSURE(ctx, ctx->s_qvis, Nmax * V);
+    ENSURE(ctx, ctx->s_rgba, Nmax * 20);
+    ENSURE(ctx, ctx->s_contrib, (size_t)RC * Sc * 4);
+    float* rays = (float*)ctx->s_rays.p; float* z = (float*)ctx->s_z.p; float* z2 = (float*)ctx->s_z2.p;
+    float* sdf = (float*)ctx->s_sdf.p; int* nn = (int*)ctx->s_nn.p; unsigned char* qv = (unsigned char*)ctx->s_qvis.p;
+    float* rgba = (float*)ctx->s_rgba.p; float* contrib = (float*)ctx->s_contrib.p;
+    for (int r0 = 0; r0 < R; r0 += RC) {
+        const int rc = (R - r0) < RC ? (R - r0) : RC;
+        int st;
+        float* oc = out_coarse + (size_t)r0 * 8;
+        if ((st = vanerf_sample_rays(ctx, tar, pix_xy + 2 * (size_t)r0, rc, ztab, Sc, rays, z, stream_))) return st;
+        if ((st = vanerf_geom_query(ctx, tar, rays, z, rc, Sc, nullptr, sdf, nullptr, nn, qv, stream_))) return st;
+        if ((st = shade_impl(ctx, precision, td, rays, z, rc, Sc, sdf, nn, qv, rgba, nullptr, nullptr, nullptr, stream))) return st;
+        // composite writes planes (color | depth | alpha | sdf); k_pack_out interleaves them into (R,8) rows
+        ENSURE(ctx, ctx->s_tab, (size_t)RC * 6 * 4);
+        float* pl = (float*)ctx->s_tab.p;      // color (RC,3) | depth | alpha | sdf
+        if ((st = vanerf_composite(ctx, rgba, z, sdf, rc, Sc, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, contrib, stream_))) return st;
+        VANERF_LAUNCH(k_pack_out, cdiv(rc, 256), 256, 0, stream, pl, RC, rc, oc); CHECK_LAUNCH(ctx);
+        if (fine) {
+            float* of = out_fine + (size_t)r0 * 8;
+            if ((st = vanerf_importance(ctx, contrib, z, rc, Sc, utab, Sf, 0, nullptr, z2, stream_))) return st;
+            if ((st = vanerf_geom_query(ctx, tar, rays, z2, rc, S2, nullptr, sdf, nullptr, nn, qv, stream_))) return st;
+            if ((st = shade_impl(ctx, precision, td, rays, z2, rc, S2, sdf, nn, qv, rgba, nullptr, nullptr, nullptr, stream))) return st;
+            if ((st = vanerf_composite(ctx, rgba, z2, sdf, rc, S2, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, nullptr, stream_))) return st;
+            VANERF_LAUNCH(k_pack_out, cdiv(rc, 256), 256, 0, stream, pl, RC, rc, of); CHECK_LAUNCH(ctx);
+        }
+    }
+    return VANERF_OK;
+}
+
+}  // extern "C"
+
+#ifndef VANERF_HOST_EMUL
+#include "mlp_tc.cuh"
+#endif

@@ -1,0 +1,263 @@
+"""Host side of the B200 render path: owns a `vanerf_ctx`, packs weights, runs the per-frame setup and launches the
+kernels through the C ABI (include/vanerf_b200.h).  torch is used for device memory, streams and the few per-frame
+library ops the reference also leaves to torch (3x3 / 4x4 inverses, the TexVisFusion global-feature convolutions,
+src/networks.py:273-279); everything per-ray / per-sample runs in libvanerf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import weights as W
+
+NUM_VERT = 1558
+
+
+def _np32(t):
+    if isinstance(t, torch.Tensor):
+        t = t.detach().float().cpu().numpy()
+    return np.ascontiguousarray(t, dtype=np.float32)
+
+
+class Renderer:
+    def __init__(self, device="cuda:0", lib: Optional[L.Lib] = None):
+        self.lib = lib or L.get_lib()
+        self.device = torch.device(device)
+        if not self.lib.emulated and self.device.type != "cuda":
+            raise L.VanerfError("vanerf_b200 runs on CUDA devices only (no CPU fallback)")
+        self.ctx = C.c_void_p()
+        dev_index = self.device.index or 0
+        self.lib.check(None, self.lib.dll.vanerf_ctx_create(C.byref(self.ctx), dev_index), "vanerf_ctx_create")
+        self.sd: Optional[Dict[str, torch.Tensor]] = None
+        self.frame = None
+        self._keep = []          # host arrays referenced by C structs during a call
+        self._tabs = {}
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                self.lib.dll.vanerf_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    @property
+    def stream(self):
+        if self.lib.emulated:
+            return None
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ptr(self, t: Optional[torch.Tensor]):
+        if t is None:
+            return None
+        assert t.is_contiguous()
+        if not self.lib.emulated:
+            assert t.is_cuda, "device tensor expected"
+        return C.c_void_p(t.data_ptr())
+
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.dll.vanerf_launch_count(self.ctx))
+
+    def linspace(self, n: int) -> torch.Tensor:
+        """torch.linspace(0,1,n) computed by torch on the host like the reference (src/model.py:1222,1440)."""
+        if n not in self._tabs:
+            self._tabs[n] = torch.linspace(0.0, 1.0, steps=n).to(self.device)
+        return self._tabs[n]
+
+    # ------------------------------------------------------------------------------------------ weights
+    def load_state_dict(self, state_dict):
+        """Accepts the reference `VANeRF.state_dict()` / a Lightning checkpoint's `state_dict` (numpy or torch)."""
+        sd = W.strip_prefix(state_dict)
+        folded = W.fold(sd)
+        keep = []
+
+        def lin(tag):
+            w = np.ascontiguousarray(folded[tag + ".w"], np.float32)
+            b = folded.get(tag + ".b")
+            keep.append(w)
+            v = L.VLinear()
+            v.w = w.ctypes.data
+            v.out_dim, v.in_dim = w.shape
+            if b is not None:
+                b = np.ascontiguousarray(b, np.float32)
+                keep.append(b)
+                v.b = b.ctypes.data
+            return v
+        vw = L.VWeights()
+        for name, tags in [("geo_at", ["geo_at0", "geo_at1"]), ("geo_f", ["geo_f0", "geo_f1"]),
+                           ("geo8_at", ["geo8_at0", "geo8_at1"]), ("geo8_f", ["geo8_f0", "geo8_f1"]),
+                           ("mlp", ["mlp0", "mlp1", "mlp2", "mlp3"]), ("post", ["post0", "post1", "post2"]),
+                           ("tex_at", ["tex_at0", "tex_at1"]), ("tex_f", ["tex_f0", "tex_f1"]),
+                           ("ray", ["ray0", "ray1"]), ("base", ["base0", "base1"]), ("vis1", ["vis10", "vis11"]),
+                           ("vis2", ["vis20", "vis21"]), ("outl", ["outl0", "outl1", "outl2"])]:
+            arr = getattr(vw, name)
+            for i, t in enumerate(tags):
+                arr[i] = lin(t)
+        vw.compress = lin("compress")
+        vw.ani_al = float(folded["ani_al"][0])
+        vw.sigmoid_beta = float(folded["sigmoid_beta"][0])
+        self.lib.check(self.ctx, self.lib.dll.vanerf_load_weights(self.ctx, C.byref(vw), self.stream), "vanerf_load_weights")
+        # per-frame TexVisFusion convolution stacks stay in torch (cuDNN), on the device
+        self.sd = {k: torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v).float().to(self.device)
+                   for k, v in sd.items() if k.startswith(("tex_vis_fusion.fconv3", "tex_vis_fusion.fconv4", "tex_vis_fusion.fconv_gt"))}
+        self.sigmoid_beta = max(2e-3, float(folded["sigmoid_beta"][0]))
+
+    # ------------------------------------------------------------------------------------------ per frame
+    @torch.no_grad()
+    def global_vertex_feature(self, img, feat_tex):
+        """TexVisFusion global feature per vertex, (V,1558,18) (src/networks.py:273-279).  LayerNorm shapes follow
+        the actual map sizes."""
+        sd = self.sd
+
+        def stack(x, pre):
+            x = F.conv2d(x, sd[pre + ".0.weight"], padding=1)
+            x = F.relu(F.layer_norm(x, x.shape[-2:], sd[pre + ".1.weight"], sd[pre + ".1.bias"], 1e-6))
+            x = F.conv2d(x, sd[pre + ".3.weight"], padding=1)
+            x = F.relu(F.layer_norm(x, x.shape[-2:], sd[pre + ".4.weight"], sd[pre + ".4.bias"], 1e-6))
+            return F.adaptive_avg_pool2d(x, 3)
+        gf = stack(feat_tex, "tex_vis_fusion.fconv3")
+        gi = stack(img, "tex_vis_fusion.fconv4")
+        g = torch.cat([gi.reshape(*gi.shape[:2], -1), gf.reshape(*gf.shape[:2], -1)], -1)
+        p = "tex_vis_fusion.fconv_gt"
+        x = F.conv1d(g, sd[p + ".0.weight"], padding=1)
+        x = F.relu(F.layer_norm(x, (18,), sd[p + ".1.weight"], sd[p + ".1.bias"], 1e-6))
+        x = F.conv1d(x, sd[p + ".3.weight"], padding=1)
+        x = F.relu(F.layer_norm(x, (18,), sd[p + ".4.weight"], sd[p + ".4.bias"], 1e-6))
+        return x.contiguous()
+
+    @torch.no_grad()
+    def set_frame(self, img, cam_in, targets, sp_data, feat_geo, feat_tex, src_foreground_mask):
+        """Per-frame setup from the reference-layout inputs (B = 1): img (V,3,H,W), cam_in dict (decode_batch,
+        src/model.py:313-317), targets{vert_world,face_world}, sp_data{extrin,kpt3d}, feat_geo [g0,g1], feat_tex,
+        src_foreground_mask (1,V,1,H,W) bool."""
+        assert self.sd is not None, "load_state_dict first"
+        V = img.shape[0]
+        H, Wd = int(cam_in["height"]), int(cam_in["width"])
+        dev = self.device
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        img_d, g0, g1, tx = f32(img), f32(feat_geo[0]), f32(feat_geo[1]), f32(feat_tex)
+        fg = src_foreground_mask.reshape(V, H, Wd).to(dev).to(torch.uint8).contiguous()
+        gfeat = self.global_vertex_feature(img_d, tx)
+        KRT = cam_in["KRT"].detach().float()
+        src_pos = torch.inverse(KRT)[:, :3, 3]                        # src/model.py:937-938
+        znear, zfar = float(cam_in["znear"]), float(cam_in["zfar"])
+        verts = _np32(targets["vert_world"]).reshape(-1, 3)
+        faces = np.ascontiguousarray(targets["face_world"].detach().cpu().numpy().reshape(-1, 3).astype(np.int32))
+        host = dict(KRT=_np32(KRT), extrin=_np32(sp_data["extrin"]), src_pos=_np32(src_pos),
+                    kpt=_np32(sp_data["kpt3d"]).reshape(-1, 3), verts=verts, faces=faces)
+        fr = L.VFrame()
+        fr.n_views, fr.height, fr.width = V, H, Wd
+        fr.znear, fr.zfar, fr.z_range = znear, zfar, float(np.float32(zfar - znear))
+        fr.KRT, fr.extrin = host["KRT"].ctypes.data, host["extrin"].ctypes.data
+        fr.src_cam_pos, fr.kpt3d = host["src_pos"].ctypes.data, host["kpt"].ctypes.data
+        fr.verts, fr.faces = verts.ctypes.data, faces.ctypes.data
+        fr.n_verts, fr.n_faces = verts.shape[0], faces.shape[0]
+        fr.img, fr.fg_mask = img_d.data_ptr(), fg.data_ptr()
+        fr.feat_geo0, fr.g0_h, fr.g0_w = g0.data_ptr(), g0.shape[2], g0.shape[3]
+        fr.feat_geo1, fr.g1_h, fr.g1_w = g1.data_ptr(), g1.shape[2], g1.shape[3]
+        fr.feat_tex, fr.t_h, fr.t_w = tx.data_ptr(), tx.shape[2], tx.shape[3]
+        fr.vert_gfeat = gfeat.data_ptr()
+        vert_vis = self.empty((V, verts.shape[0]))
+        self.lib.check(self.ctx, self.lib.dll.vanerf_frame_setup(self.ctx, C.byref(fr), self._ptr(vert_vis), self.stream),
+                       "vanerf_frame_setup")
+        self.frame = dict(V=V, H=H, W=Wd, znear=znear, zfar=zfar, vert_vis=vert_vis, gfeat=gfeat,
+                          inputs=(img_d, g0, g1, tx, fg))
+        return vert_vis
+
+    def make_target(self, cam_tar, bounds, znear=None, zfar=None) -> L.VTarget:
+        """Per-render 3x3 matrices by the same torch calls as the reference (src/model.py:1208-1213)."""
+        K, RT = cam_tar["K"].detach().float().cpu(), cam_tar["RT"].detach().float().cpu()
+        inv_K = torch.inverse(K[:, :3, :3]).transpose(1, 2)[0].contiguous().numpy()
+        R = RT[0, :3, :3].contiguous().numpy()
+        cam_pos = (-torch.bmm(RT[:, :3, 3][:, None], RT[:, :3, :3]))[0, 0].numpy()
+        t = L.VTarget()
+        t.inv_K[:] = inv_K.reshape(-1).tolist()
+        t.R[:] = R.reshape(-1).tolist()
+        t.cam_pos[:] = cam_pos.tolist()
+        t.znear = float(cam_tar.get("znear", self.frame["znear"]) if znear is None else znear)
+        t.zfar = float(cam_tar.get("zfar", self.frame["zfar"]) if zfar is None else zfar)
+        t.bounds[:] = _np32(bounds).reshape(-1).tolist()
+        return t
+
+    # ------------------------------------------------------------------------------------------ stages
+    def sample_rays(self, tar, pix_xy: torch.Tensor, n_samples: int):
+        R = pix_xy.shape[0]
+        pix = pix_xy.to(self.device, torch.int32).contiguous()
+        rays, z = self.empty((R, L.RAY_STRIDE)), self.empty((R, n_samples))
+        self.lib.check(self.ctx, self.lib.dll.vanerf_sample_rays(self.ctx, C.byref(tar), self._ptr(pix), R,
+                       self._ptr(self.linspace(n_samples)), n_samples, self._ptr(rays), self._ptr(z), self.stream), "vanerf_sample_rays")
+        return rays, z
+
+    def geom_query(self, tar, rays, z, want_pts=True):
+        R, S = z.shape
+        N, V = R * S, self.frame["V"]
+        pts = self.empty((N, 3)) if want_pts else None
+        sdf, face, nn = self.empty((N,)), self.empty((N,), torch.int32), self.empty((N,), torch.int32)
+        qvis = self.empty((V, N), torch.uint8)
+        self.lib.check(self.ctx, self.lib.dll.vanerf_geom_query(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S,
+                       self._ptr(pts), self._ptr(sdf), self._ptr(face), self._ptr(nn), self._ptr(qvis), self.stream), "vanerf_geom_query")
+        return dict(pts=pts, sdf=sdf, face=face, nn=nn, qvis=qvis)
+
+    def shade(self, tar, rays, z, geo, precision=L.FP32, want_raw=True, want_latent=False):
+        R, S = z.shape
+        N = R * S
+        rgba, valid = self.empty((N, 5)), self.empty((N,), torch.uint8)
+        raw = self.empty((N, 5)) if want_raw else None
+        if want_latent:
+            lat = self.empty((N, 128))
+            st = self.lib.dll.vanerf_shade_debug(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
+                                                 self._ptr(geo["nn"]), self._ptr(geo["qvis"]), self._ptr(rgba), self._ptr(valid),
+                                                 self._ptr(raw), self._ptr(lat), self.stream)
+            self.lib.check(self.ctx, st, "vanerf_shade_debug")
+            return rgba, valid, raw, lat
+        st = self.lib.dll.vanerf_shade(self.ctx, precision, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
+                                       self._ptr(geo["nn"]), self._ptr(geo["qvis"]), self._ptr(rgba), self._ptr(valid), self._ptr(raw), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_shade")
+        return rgba, valid, raw
+
+    def composite(self, rgba, z, mesh_sdf):
+        R, S = z.shape
+        out = dict(color=self.empty((R, 3)), depth=self.empty((R,)), alpha=self.empty((R,)), sdf=self.empty((R,)),
+                   contrib=self.empty((R, S)))
+        st = self.lib.dll.vanerf_composite(self.ctx, self._ptr(rgba), self._ptr(z), self._ptr(mesh_sdf), R, S, self._ptr(out["color"]),
+                                           self._ptr(out["depth"]), self._ptr(out["alpha"]), self._ptr(out["sdf"]),
+                                           self._ptr(out["contrib"]), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_composite")
+        return out
+
+    def importance(self, contrib, z, n_fine: int, u: Optional[torch.Tensor] = None):
+        R, S = z.shape
+        per_ray = 0
+        if u is None:
+            u = self.linspace(n_fine)
+        elif u.dim() == 2:
+            per_ray = 1
+        u = u.to(self.device, torch.float32).contiguous()
+        z_f, z_all = self.empty((R, n_fine)), self.empty((R, S + n_fine))
+        st = self.lib.dll.vanerf_importance(self.ctx, self._ptr(contrib), self._ptr(z), R, S, self._ptr(u), n_fine, per_ray,
+                                            self._ptr(z_f), self._ptr(z_all), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_importance")
+        return z_f, z_all
+
+    def render_rays(self, tar, pix_xy, n_coarse=64, n_fine=64, fine=True, precision=L.FP32):
+        """One call for a ray batch: coarse pass, importance sampling, fine pass (src/model.py:1103-1360).
+        Returns (R,8) rows [r,g,b,depth,alpha,sdf,0,0] for the coarse and the fine pass."""
+        R = pix_xy.shape[0]
+        pix = pix_xy.to(self.device, torch.int32).contiguous()
+        oc = self.empty((R, 8))
+        of = self.empty((R, 8)) if fine else None
+        st = self.lib.dll.vanerf_render_rays(self.ctx, precision, C.byref(tar), self._ptr(pix), R, n_coarse, n_fine, int(fine),
+                                             self._ptr(self.linspace(n_coarse)), self._ptr(self.linspace(n_fine)) if fine else None,
+                                             self._ptr(oc), self._ptr(of), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_render_rays")
+        return oc, of
