@@ -143,6 +143,11 @@ int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int
                       const float* u, int32_t n_fine, int32_t u_per_ray, float* z_fine_only, float* z_out,
                       void* stream);
 
+/* Same sampler with the reference's own argument convention: contrib_inner dev (R, D-2) = contrib[..., 1:-1],
+ * z_mid dev (R, D-1); z_fine dev (R, n_fine) out, no merge. */
+int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const float* z_mid, int32_t n_rays, int32_t n_depths,
+                          const float* u, int32_t n_fine, int32_t u_per_ray, float* z_fine, void* stream);
+
 /* One call for VANeRF.batch_render_pifu_nerf's ray batch (src/model.py:1103-1422, inference branch):
  * rays -> coarse pass -> composite -> importance -> fine pass -> composite, chunked internally.
  * ztab dev (n_coarse) = linspace(0,1,n_coarse), utab dev (n_fine) = linspace(0,1,n_fine) (uniform=True).
@@ -158,6 +163,19 @@ size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t n_rays, int32_t n_sam
 int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t n_rays,
                        int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba,
                        uint8_t* valid, float* raw_out, float* latent, void* stream);
+
+/* VANeRF.query on explicit points (src/model.py:748-877): pts, view dev (N,3).  sdf_in / qvis_in: optional
+ * caller-provided query_sdf (N) / query_vis (V,N) (the reference passes them in); NULL = computed from the mesh.
+ * raw_out dev (N,5) = [o0,o1,r,g,b], valid dev (N), rgba dev (N,5) (eval_func layout); outputs may be NULL. */
+int vanerf_query_points(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* pts, const float* view,
+                        int32_t n_points, const float* sdf_in, const uint8_t* qvis_in, float* raw_out, uint8_t* valid,
+                        float* rgba, void* stream);
+
+/* Per-kernel-class device timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * numbers).  vanerf_timing_read synchronises the recorded events; ms_out / count_out have 7 entries:
+ * frame setup, rays, geometry, gather, mlp, composite, importance. */
+int vanerf_timing_enable(vanerf_ctx* ctx, int on);
+int vanerf_timing_read(vanerf_ctx* ctx, double* ms_out, int64_t* count_out, int reset);
 
 /* Number of kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vanerf_launch_count(const vanerf_ctx* ctx);

@@ -35,7 +35,7 @@ def lib():
         _lib.vo_point_mesh_distance.argtypes = [P, I64, P, P, I64, P, P]
         _lib.vo_check_sign.argtypes = [P, I64, P, P, I64, P]
         _lib.vo_knn1.argtypes = [P, I64, P, I64, P]
-        _lib.vo_rasterize.argtypes = [P, P, I64, ctypes.c_int, P]
+        _lib.vo_rasterize.argtypes = [P, P, I64, ctypes.c_int, ctypes.c_int, ctypes.c_int, P]
         for f in (_lib.vo_point_mesh_distance, _lib.vo_check_sign, _lib.vo_knn1, _lib.vo_rasterize):
             f.restype = None
     return _lib
@@ -108,7 +108,12 @@ def knn1_np(pts, verts):
 def rasterize_np(xyz, faces, image_size=256):
     xyz, faces = _f32(xyz).reshape(-1, 3), _i64(faces).reshape(-1, 3)
     out = np.empty((image_size, image_size), np.int64)
-    lib().vo_rasterize(_ptr(xyz), _ptr(faces), faces.shape[0], int(image_size), _ptr(out))
+    L = lib()
+
+    def run(se):
+        L.vo_rasterize(_ptr(xyz), _ptr(faces), faces.shape[0], int(image_size), se[0], se[1], _ptr(out))
+    with ThreadPoolExecutor(_NT) as ex:
+        list(ex.map(run, _split(image_size, _NT * 4)))
     return out
 
 

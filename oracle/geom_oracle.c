@@ -131,9 +131,9 @@ static inline float edge_fn(float px, float py, float ax, float ay, float bx, fl
 
 /* pytorch3d naive rasteriser restated: square image S, NDC +X left / +Y up, pixel (row i, col j) centre at
  * (1-(2j+1)/S, 1-(2i+1)/S); K=1 nearest pz, ties -> lowest face index; -1 = empty. */
-void vo_rasterize(const float* xyz, const int64_t* faces, int64_t F, int S, int64_t* pix_to_face) {
+void vo_rasterize(const float* xyz, const int64_t* faces, int64_t F, int S, int row0, int row1, int64_t* pix_to_face) {
     const float kEps = 1e-8f;
-    for (int i = 0; i < S; ++i) {
+    for (int i = row0; i < row1; ++i) {
         for (int j = 0; j < S; ++j) {
             int yi = S - 1 - i, xi = S - 1 - j;
             float pxf = -1.0f + (2.0f * (float)xi + 1.0f) / (float)S;

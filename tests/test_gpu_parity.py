@@ -1,0 +1,111 @@
+"""Parity tests proper: the CUDA library through the C ABI on a B200 against the oracle (same seeded inputs), against
+the golden vectors of the reference itself, and - at BASELINE.json's full size - through size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+import parity
+from vanerf_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("H,W,V,mode,layout,npix", [
+    (256, 256, 1, "ref", "narrow", 8),
+    (256, 256, 1, "stress", "narrow", 8),
+    (512, 334, 3, "ref", "narrow", 10),
+    (512, 334, 3, "stress", "narrow", 12),
+    (512, 334, 3, "stress", "bvv", 12),
+    (512, 334, 4, "stress", "narrow", 6),
+    (512, 334, 2, "stress", "bvv", 6),
+])
+def test_cuda_stages_match_oracle_fp32(cuda_lib, H, W, V, mode, layout, npix):
+    sc, inp, sd = parity.build_case(H, W, V, mode=mode, layout=layout)
+    r, vert_vis = parity.make_renderer(inp, sd, "cuda:0")
+    pix = parity.lattice_pixels(H, W, npix)
+    errs, oo, ot = parity.check_all(r, vert_vis, inp, sd, pix, precision=L.FP32)
+    assert ot["valid"].any() and not ot["valid"].all()
+    parity.check_render_rays(r, inp, oo, pix, tol_fine=5e-3)
+    assert r.launches > 0
+    print("max-abs errors", {k: f"{v:.2e}" for k, v in errs.items()})
+
+
+@pytest.mark.parametrize("name", ["v1_256_ref", "v3_512x334_ref", "v3_512x334_str", "v3_bvv_str"])
+def test_cuda_surface_matches_reference_golden(cuda_lib, name):
+    from test_model_surface import run_surface_case
+    run_surface_case(name, "cuda:0", None)
+
+
+def test_cuda_ragged_and_tiny_sizes(cuda_lib):
+    from oracle import oracle_torch as OT
+    sc, inp, sd = parity.build_case(256, 256, 2, mode="stress")
+    r, _ = parity.make_renderer(inp, sd, "cuda:0")
+    orc = OT.Oracle(sd, inp)
+    for n_rays, S in [(1, 8), (7, 24), (33, 65), (130, 64)]:
+        pix = parity.lattice_pixels(256, 256, 12)[:n_rays]
+        ot = {}
+        orc.render(fine=False, pixels=pix, S_c=S, taps=ot)
+        tar = r.make_target(inp["cam_tar"], inp["bounds"])
+        rays, z = r.sample_rays(tar, torch.from_numpy(pix), S)
+        parity.assert_exact("z", z.cpu().numpy(), ot["z"])
+        geo = r.geom_query(tar, rays, z)
+        parity.assert_exact("face", geo["face"].cpu().numpy().astype(np.int64), ot["geo"]["face"])
+        rgba, valid, raw = r.shade(tar, rays, z, geo)
+        parity.assert_exact("valid", valid.cpu().numpy() > 0, ot["valid"])
+        parity.assert_close("rgba", rgba.cpu().numpy(), ot["rgba"], parity.TOL_FP32)
+
+
+def test_cuda_full_view_properties(cuda_lib):
+    """Config B size (334x512, V=3, 64+64): properties that do not need the oracle at full size + an oracle spot check."""
+    H, W, V = 512, 334, 3
+    sc, inp, sd = parity.build_case(H, W, V, mode="stress")
+    r, vert_vis = parity.make_renderer(inp, sd, "cuda:0")
+    tar = r.make_target(inp["cam_tar"], inp["bounds"])
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    pix = torch.stack([xs, ys], -1).reshape(-1, 2)
+    R = pix.shape[0]
+    assert R == 171008
+    rays, z = r.sample_rays(tar, pix, 64)
+    zc = z.cpu().numpy()
+    assert np.isfinite(zc).all() and (np.diff(zc, axis=1) > 0).all(), "coarse depths strictly increasing"
+    # linearity of the depth table: z = near + (far-near)*t reproduced on the host bit for bit
+    rn = rays.cpu().numpy()
+    t = torch.linspace(0, 1, 64).numpy()
+    assert np.array_equal(zc, (rn[:, 3:4] + (rn[:, 4:5] - rn[:, 3:4]) * t[None]).astype(np.float32))
+    oc, of = r.render_rays(tar, pix, 64, 64, True)
+    oc, of = oc.cpu().numpy(), of.cpu().numpy()
+    assert np.isfinite(oc).all() and np.isfinite(of).all()
+    assert np.abs(oc[:, 4] - 1).max() < 1e-4 and np.abs(of[:, 4] - 1).max() < 1e-4, "alpha == 1 (last interval is 1e10, B-7)"
+    assert (of[:, 3] > 0.5).all() and (of[:, 3] < 1.6).all(), "depth inside the frustum"
+    # the chunked full-view call must equal the same rays rendered as a small batch (chunk-boundary independence)
+    sel = np.random.RandomState(0).choice(R, 96, replace=False)
+    oc2, of2 = r.render_rays(tar, pix[sel], 64, 64, True)
+    assert np.array_equal(oc2.cpu().numpy(), oc[sel]) and np.array_equal(of2.cpu().numpy(), of[sel])
+    # oracle spot check on those rays
+    from oracle import oracle_torch as OT
+    oo = OT.Oracle(sd, inp).render(fine=True, pixels=pix[sel].numpy())
+    parity.assert_close("full-view tex_fg vs oracle", oc[sel, :3], oo["tex_fg"], 1e-3)
+    parity.assert_close("full-view tex_fg_fine vs oracle", of[sel, :3], oo["tex_fg_fine"], 5e-3)
+
+
+def test_cuda_frame_switch_and_idempotence(cuda_lib):
+    """Two frames through one context (render_dynamic usage): results depend only on the current frame."""
+    sc0, inp0, sd = parity.build_case(256, 256, 3, mode="stress", frame=0)
+    sc1, inp1, _ = parity.build_case(256, 256, 3, mode="stress", frame=5)
+    r, _ = parity.make_renderer(inp0, sd, "cuda:0")
+    pix = torch.from_numpy(parity.lattice_pixels(256, 256, 8))
+    tar = r.make_target(inp0["cam_tar"], inp0["bounds"])
+    a0 = r.render_rays(tar, pix)[1].clone()
+    mv = lambda t: t.to("cuda:0")
+    r.set_frame(mv(inp1["img"]), inp1["cam_in"], inp1["targets"], inp1["sp_data"], [mv(t) for t in inp1["feat_geo"]], mv(inp1["feat_tex"]), mv(inp1["src_foreground_mask"]))
+    a1 = r.render_rays(r.make_target(inp1["cam_tar"], inp1["bounds"]), pix)[1].clone()
+    r.set_frame(mv(inp0["img"]), inp0["cam_in"], inp0["targets"], inp0["sp_data"], [mv(t) for t in inp0["feat_geo"]], mv(inp0["feat_tex"]), mv(inp0["src_foreground_mask"]))
+    a2 = r.render_rays(tar, pix)[1]
+    assert torch.equal(a0, a2) and not torch.equal(a0, a1)
+
+
+def test_cuda_errors_are_loud(cuda_lib):
+    from vanerf_b200.renderer import Renderer
+    r = Renderer("cuda:0")
+    with pytest.raises(L.VanerfError):
+        r.lib.check(r.ctx, r.lib.dll.vanerf_geom_query(r.ctx, None, None, None, 1, 1, None, None, None, None, None, None), "geom")

@@ -30,7 +30,7 @@ def build_cuda(force=False, verbose=False):
     if not force and not _stale(CUDA_SO):
         return CUDA_SO
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "vanerf_b200.cu"), "-lcuda"]
+           "-Xcompiler", "-fPIC", "-shared", "-o", CUDA_SO, os.path.join(CSRC, "vanerf_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

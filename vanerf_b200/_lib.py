@@ -63,7 +63,11 @@ PROTOTYPES = {
     "vanerf_shade_debug": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vanerf_composite": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vanerf_importance": (C.c_int, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _P]),
+    "vanerf_importance_mid": (C.c_int, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "vanerf_render_rays": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "vanerf_query_points": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "vanerf_timing_enable": (C.c_int, [_P, C.c_int]),
+    "vanerf_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.c_int]),
     "vanerf_scratch_bytes": (C.c_size_t, [_P, _I, _I]),
     "vanerf_launch_count": (_I64, [_P]),
 }

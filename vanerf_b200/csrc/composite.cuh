@@ -82,8 +82,8 @@ k_composite(const float* __restrict__ rgba, const float* __restrict__ z, const f
 
 // One warp per ray.  Dynamic shared memory per warp: cdf[S-1] | zmid[S-1] | vals[S+nf]  (floats).
 __global__ void __launch_bounds__(COMP_WARPS * 32)
-k_importance(const float* __restrict__ contrib, const float* __restrict__ z, int R, int S, const float* __restrict__ u,
-             int nf, int u_per_ray, float* __restrict__ z_fine_only, float* __restrict__ z_out) {
+k_importance(const float* __restrict__ contrib, const float* __restrict__ z, const float* __restrict__ zmid_in, int R, int S,
+             const float* __restrict__ u, int nf, int u_per_ray, float* __restrict__ z_fine_only, float* __restrict__ z_out) {
     DYN_SMEM(float, sm);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int per_warp = 2 * (S - 1) + (S + nf);
@@ -97,11 +97,16 @@ k_importance(const float* __restrict__ contrib, const float* __restrict__ z, int
         const int r = r0 + warp0;
         const bool live = r < R;
         const int rr = live ? r : R - 1;
-        const float* cr = contrib + (size_t)rr * S;
-        const float* zr = z + (size_t)rr * S;
+        // reference calling convention (zmid_in != NULL): contrib holds the S-2 inner bins, zmid_in the S-1 midpoints
+        const float* cr = zmid_in ? contrib + (size_t)rr * (S - 2) - 1 : contrib + (size_t)rr * S;
+        const float* zr = zmid_in ? nullptr : z + (size_t)rr * S;
         __syncwarp();
-        for (int i = lane; i < S - 1; i += 32) zmid[i] = xmul(0.5f, xadd(zr[i + 1], zr[i]));
-        for (int i = lane; i < S; i += 32) vals[i] = zr[i];
+        if (zmid_in) {
+            for (int i = lane; i < S - 1; i += 32) zmid[i] = zmid_in[(size_t)rr * (S - 1) + i];
+        } else {
+            for (int i = lane; i < S - 1; i += 32) zmid[i] = xmul(0.5f, xadd(zr[i + 1], zr[i]));
+            for (int i = lane; i < S; i += 32) vals[i] = zr[i];
+        }
         // left-to-right sums (every lane computes the same values; 2*(S-2) dependent adds)
         float tot = 0.0f;
         for (int i = 0; i < nb; ++i) tot = xadd(tot, xadd(cr[1 + i], 1e-5f));
@@ -132,6 +137,7 @@ k_importance(const float* __restrict__ contrib, const float* __restrict__ z, int
             if (z_fine_only && live) z_fine_only[(size_t)r * nf + j] = zf;
         }
         __syncwarp();
+        if (!z_out) continue;
         const int n = S + nf;
         for (int i = lane; i < n; i += 32) {
             const float x = vals[i];

@@ -48,8 +48,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // rec: (n_samples_in_chunk * V, REC_STRIDE).  sample0 = first global sample index of this chunk.
 // valid_out: optional (N) 0/1 = VANeRF.query's `valid`.
 __global__ void __launch_bounds__(GATHER_THREADS)
-k_gather(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z, int S,
-         long long sample0, int n_chunk, long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,
+k_gather(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
+         const float* __restrict__ pts_in, const float* __restrict__ view_in, int S, long long sample0, int n_chunk, long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,
          const unsigned char* __restrict__ qvis, float* __restrict__ rec, unsigned char* __restrict__ valid_out) {
     const int lane = threadIdx.x & 15;
     const int group = (blockIdx.x * GATHER_THREADS + threadIdx.x) >> 4;
@@ -57,10 +57,15 @@ k_gather(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float
     const int V = fr.V;
     for (int i = group; i < n_chunk; i += n_groups) {
         const long long n = sample0 + i;
-        const int r = (int)(n / S);
-        const float* ray = rays + (size_t)r * VANERF_RAY_STRIDE;
         float p[3];
-        sample_point(ray, tar.cam_pos, z[n], p);
+        const float* ray;
+        if (pts_in) {            // explicit points + view directions (VANeRF.query called directly)
+            p[0] = pts_in[3 * n]; p[1] = pts_in[3 * n + 1]; p[2] = pts_in[3 * n + 2];
+            ray = view_in + 3 * n;
+        } else {
+            ray = rays + (size_t)(n / S) * VANERF_RAY_STRIDE;
+            sample_point(ray, tar.cam_pos, z[n], p);
+        }
         // ---- pass 1: projections, masks, smooth boundary weights (all views; lane-redundant, registers only)
         ViewProj pr[MAXV];
         float pw[MAXV];

@@ -202,15 +202,17 @@ __device__ __forceinline__ void bary_of_projection(const FrameDev& fr, const flo
 }
 
 // One thread per sample.  Outputs may be NULL.
+// pts_in != NULL: explicit query points (VANeRF.query called directly) instead of cam_pos + dir * z.
 __global__ void k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
-                             int R, int S, float* __restrict__ pts, float* __restrict__ sdf, int* __restrict__ face,
-                             int* __restrict__ nn_vert, unsigned char* __restrict__ qvis) {
+                             const float* __restrict__ pts_in, int R, int S, float* __restrict__ pts, float* __restrict__ sdf,
+                             int* __restrict__ face, int* __restrict__ nn_vert, unsigned char* __restrict__ qvis) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N = (long long)R * S;
     if (n >= N) return;
     const int r = (int)(n / S);
     float p[3];
-    sample_point(rays + (size_t)r * VANERF_RAY_STRIDE, tar.cam_pos, z[n], p);
+    if (pts_in) { p[0] = pts_in[3 * n]; p[1] = pts_in[3 * n + 1]; p[2] = pts_in[3 * n + 2]; }
+    else sample_point(rays + (size_t)r * VANERF_RAY_STRIDE, tar.cam_pos, z[n], p);
     if (pts) { pts[3 * n] = p[0]; pts[3 * n + 1] = p[1]; pts[3 * n + 2] = p[2]; }
     float d2; int f;
     closest_face(fr, p, d2, f);

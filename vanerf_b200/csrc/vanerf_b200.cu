@@ -19,10 +19,23 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+enum KernelClass { KCL_SETUP = 0, KCL_RAYS, KCL_GEOM, KCL_GATHER, KCL_MLP, KCL_COMPOSITE, KCL_IMPORTANCE, KCL_COUNT };
+
+#ifndef VANERF_HOST_EMUL
+struct TimedEv { int kc; cudaEvent_t a, b; };
+#endif
+
 struct vanerf_ctx {
     int device = 0, sm_count = 148;
     int64_t launches = 0;
     char err[512] = {0};
+    // optional per-kernel-class CUDA-event timing (bench.py roofline numbers)
+    bool timing = false;
+    double t_ms[KCL_COUNT] = {0};
+    int64_t t_cnt[KCL_COUNT] = {0};
+#ifndef VANERF_HOST_EMUL
+    std::vector<TimedEv> evs;
+#endif
     // weights
     DevBuf wblob, netdev, tcw;
     NetDev h_net;
@@ -65,6 +78,19 @@ static int ensure(vanerf_ctx* ctx, DevBuf& b, size_t bytes) {
 #define CHECK_LAUNCH(ctx) do { (ctx)->launches++; CUDA_TRY((ctx), cudaGetLastError()); } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Brackets the launches of one kernel class with CUDA events on the launching stream when timing is enabled.
+struct TimedScope {
+#ifndef VANERF_HOST_EMUL
+    vanerf_ctx* c; cudaStream_t s; TimedEv e; bool on;
+    TimedScope(vanerf_ctx* ctx, int kc, cudaStream_t st) : c(ctx), s(st), on(ctx->timing) {
+        if (on) { e.kc = kc; cudaEventCreate(&e.a); cudaEventCreate(&e.b); cudaEventRecord(e.a, s); }
+    }
+    ~TimedScope() { if (on) { cudaEventRecord(e.b, s); c->evs.push_back(e); } }
+#else
+    TimedScope(vanerf_ctx*, int, cudaStream_t) {}
+#endif
+};
 
 extern "C" {
 
@@ -223,6 +249,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     fr.kpt_cam = (const float*)ctx->kpt_cam.p;
 
     const int T = 256;
+    TimedScope ts(ctx, KCL_SETUP, stream);
     VANERF_LAUNCH(k_repack_nhwc, cdiv(g0n, T), T, 0, stream, f->feat_geo0, (float*)ctx->geo0.p, V, 64, fr.g0h, fr.g0w); CHECK_LAUNCH(ctx);
     VANERF_LAUNCH(k_repack_nhwc, cdiv(g1n, T), T, 0, stream, f->feat_geo1, (float*)ctx->geo1.p, V, 8, fr.g1h, fr.g1w); CHECK_LAUNCH(ctx);
     VANERF_LAUNCH(k_repack_nhwc, cdiv(txn, T), T, 0, stream, f->feat_tex, (float*)ctx->tex.p, V, 8, fr.th, fr.tw); CHECK_LAUNCH(ctx);
@@ -257,6 +284,7 @@ static TargetDev make_target(const vanerf_target* t) {
 int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t R, const float* ztab,
                        int32_t S, float* rays, float* z, void* stream) {
     if (!ctx || !tar || !pix_xy || !ztab || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_sample_rays");
+    TimedScope ts(ctx, KCL_RAYS, (cudaStream_t)stream);
     VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ztab, S, rays, z);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
@@ -267,16 +295,20 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
     if (!ctx || !tar || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_geom_query");
     if (!ctx->have_frame) return VANERF_ERR_STATE;
     const long long N = (long long)R * S;
-    VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, R, S, pts, sdf, face, nn_vert, qvis);
+    TimedScope ts(ctx, KCL_GEOM, (cudaStream_t)stream);
+    VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, (const float*)nullptr, R, S, pts,
+                  sdf, face, nn_vert, qvis);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
 }
 
 #define SHADE_CHUNK 65536      // samples per gather/MLP round; records: chunk * V * 1232 B
 
+// pts_in/view_in != NULL: explicit points and view directions ((N,3) each, R*S == N) instead of rays + depths
 static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const float* rays, const float* z, int R, int S,
                       const float* sdf, const int* nn, const unsigned char* qvis, float* rgba, unsigned char* valid,
-                      float* raw_out, float* dbg_latent, cudaStream_t stream) {
+                      float* raw_out, float* dbg_latent, cudaStream_t stream, const float* pts_in = nullptr,
+                      const float* view_in = nullptr) {
     const long long N = (long long)R * S;
     const int V = ctx->fr.V;
     const int chunk = (int)(N < SHADE_CHUNK ? N : SHADE_CHUNK);
@@ -290,9 +322,13 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
     for (long long s0 = 0; s0 < N; s0 += chunk) {
         const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
         const int gblocks = min(cdiv(nc, GATHER_THREADS / 16), ctx->sm_count * 8);
-        VANERF_LAUNCH(k_gather, gblocks, GATHER_THREADS, 0, stream, ctx->fr, td, rays, z, S, s0, nc, N, sdf, nn, qvis,
-                      (float*)ctx->rec.p, valid);
-        CHECK_LAUNCH(ctx);
+        {
+            TimedScope ts(ctx, KCL_GATHER, stream);
+            VANERF_LAUNCH(k_gather, gblocks, GATHER_THREADS, 0, stream, ctx->fr, td, rays, z, pts_in, view_in, S, s0, nc, N, sdf,
+                          nn, qvis, (float*)ctx->rec.p, valid);
+            CHECK_LAUNCH(ctx);
+        }
+        TimedScope ts(ctx, KCL_MLP, stream);
 #ifndef VANERF_HOST_EMUL
         if (precision == VANERF_BF16) {
             int rc = tc_shade_chunk(ctx, (const float*)ctx->rec.p, s0, nc, rgba, raw_out, stream);
@@ -328,12 +364,64 @@ int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* r
                       (cudaStream_t)stream);
 }
 
+// VANeRF.query called directly on arbitrary points (src/model.py:748-877): geometry + gather + networks.
+int vanerf_query_points(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* pts, const float* view,
+                        int32_t N, const float* sdf_in, const uint8_t* qvis_in, float* raw_out, uint8_t* valid, float* rgba,
+                        void* stream_) {
+    if (!ctx || !tar || !pts || !view || N <= 0) return ctx_invalid(ctx, "vanerf_query_points");
+    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int V = ctx->fr.V;
+    ENSURE(ctx, ctx->s_sdf, (size_t)N * 4);
+    ENSURE(ctx, ctx->s_nn, (size_t)N * 4);
+    ENSURE(ctx, ctx->s_qvis, (size_t)N * V);
+    const TargetDev td = make_target(tar);
+    {
+        TimedScope ts(ctx, KCL_GEOM, stream);
+        VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, td, (const float*)nullptr, (const float*)nullptr, pts, N, 1,
+                      (float*)nullptr, (float*)ctx->s_sdf.p, (int*)nullptr, (int*)ctx->s_nn.p, (unsigned char*)ctx->s_qvis.p);
+        CHECK_LAUNCH(ctx);
+    }
+    const float* sdf = sdf_in ? sdf_in : (const float*)ctx->s_sdf.p;
+    const unsigned char* qv = qvis_in ? qvis_in : (const unsigned char*)ctx->s_qvis.p;
+    return shade_impl(ctx, precision, td, nullptr, nullptr, N, 1, sdf, (const int*)ctx->s_nn.p, qv, rgba, valid, raw_out, nullptr,
+                      stream, pts, view);
+}
+
+int vanerf_timing_enable(vanerf_ctx* ctx, int on) {
+    if (!ctx) return VANERF_ERR_INVALID;
+    ctx->timing = on != 0;
+    return VANERF_OK;
+}
+
+// Synchronises the recorded events and accumulates; ms_out / count_out have 7 entries:
+// setup, rays, geom, gather, mlp, composite, importance.
+int vanerf_timing_read(vanerf_ctx* ctx, double* ms_out, int64_t* count_out, int reset) {
+    if (!ctx || !ms_out || !count_out) return VANERF_ERR_INVALID;
+#ifndef VANERF_HOST_EMUL
+    for (auto& e : ctx->evs) {
+        CUDA_TRY(ctx, cudaEventSynchronize(e.b));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e.a, e.b));
+        ctx->t_ms[e.kc] += ms;
+        ctx->t_cnt[e.kc] += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    ctx->evs.clear();
+#endif
+    for (int i = 0; i < KCL_COUNT; ++i) { ms_out[i] = ctx->t_ms[i]; count_out[i] = ctx->t_cnt[i]; }
+    if (reset) for (int i = 0; i < KCL_COUNT; ++i) { ctx->t_ms[i] = 0; ctx->t_cnt[i] = 0; }
+    return VANERF_OK;
+}
+
 int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t R, int32_t S,
                      float* color, float* depth, float* alpha, float* sdf_out, float* contrib, void* stream) {
     if (!ctx || !rgba || !z || !mesh_sdf || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_composite");
     if (S > 32 * COMP_MAX_PER_LANE) return VANERF_ERR_UNSUPPORTED;
     if (!ctx->have_weights) return VANERF_ERR_STATE;
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    TimedScope ts(ctx, KCL_COMPOSITE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_composite, blocks, COMP_WARPS * 32, 0, stream, rgba, z, mesh_sdf, R, S, ctx->h_net.beta, color, depth, alpha,
                   sdf_out, contrib);
     CHECK_LAUNCH(ctx);
@@ -343,10 +431,27 @@ int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const f
 int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int32_t R, int32_t S, const float* u,
                       int32_t nf, int32_t u_per_ray, float* z_fine_only, float* z_out, void* stream) {
     if (!ctx || !contrib || !z || !u || !z_out || R <= 0 || S < 3 || nf <= 0) return ctx_invalid(ctx, "vanerf_importance");
+    const float* zmid_in = nullptr;
     const size_t smem = (size_t)COMP_WARPS * (2 * (S - 1) + S + nf) * sizeof(float);
     if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
-    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, R, S, u, nf, u_per_ray, z_fine_only, z_out);
+    TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
+    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, zmid_in, R, S, u, nf, u_per_ray, z_fine_only, z_out);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+// Reference calling convention of VANeRF.importance_sample (src/model.py:1425-1462): contrib_inner (R, D-2),
+// z_mid (R, D-1) -> z_fine (R, n_fine); no merge.
+int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const float* z_mid, int32_t R, int32_t D, const float* u,
+                          int32_t nf, int32_t u_per_ray, float* z_fine, void* stream) {
+    if (!ctx || !contrib_inner || !z_mid || !u || !z_fine || R <= 0 || D < 3 || nf <= 0) return ctx_invalid(ctx, "vanerf_importance_mid");
+    const size_t smem = (size_t)COMP_WARPS * (2 * (D - 1) + D + nf) * sizeof(float);
+    if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
+    const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
+    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib_inner, (const float*)nullptr, z_mid, R, D, u, nf,
+                  u_per_ray, z_fine, (float*)nullptr);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
 }

@@ -249,6 +249,33 @@ class Renderer:
         self.lib.check(self.ctx, st, "vanerf_importance")
         return z_f, z_all
 
+    def query_points(self, tar, pts, view, query_sdf=None, query_vis=None, precision=L.FP32):
+        """VANeRF.query on explicit points: pts, view (N,3).  Returns raw (N,5) = [o0,o1,r,g,b], valid (N,), rgba."""
+        N = pts.shape[0]
+        pts = pts.to(self.device, torch.float32).contiguous()
+        view = view.to(self.device, torch.float32).contiguous()
+        raw, valid, rgba = self.empty((N, 5)), self.empty((N,), torch.uint8), self.empty((N, 5))
+        if query_sdf is not None:
+            query_sdf = query_sdf.to(self.device, torch.float32).contiguous()
+        if query_vis is not None:
+            query_vis = query_vis.to(self.device).to(torch.uint8).contiguous()
+        st = self.lib.dll.vanerf_query_points(self.ctx, precision, C.byref(tar), self._ptr(pts), self._ptr(view), N,
+                                              self._ptr(query_sdf), self._ptr(query_vis), self._ptr(raw), self._ptr(valid),
+                                              self._ptr(rgba), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_query_points")
+        return raw, valid, rgba
+
+    KERNEL_CLASSES = ("setup", "rays", "geom", "gather", "mlp", "composite", "importance")
+
+    def timing(self, on: bool):
+        self.lib.check(self.ctx, self.lib.dll.vanerf_timing_enable(self.ctx, int(on)), "vanerf_timing_enable")
+
+    def timing_read(self, reset=True):
+        ms = (C.c_double * 7)()
+        cnt = (C.c_int64 * 7)()
+        self.lib.check(self.ctx, self.lib.dll.vanerf_timing_read(self.ctx, ms, cnt, int(reset)), "vanerf_timing_read")
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     def render_rays(self, tar, pix_xy, n_coarse=64, n_fine=64, fine=True, precision=L.FP32):
         """One call for a ray batch: coarse pass, importance sampling, fine pass (src/model.py:1103-1360).
         Returns (R,8) rows [r,g,b,depth,alpha,sdf,0,0] for the coarse and the fine pass."""
