@@ -316,7 +316,8 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
     const size_t smem = mlp_simt_smem_floats(V) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(mlp_simt_smem_floats(MAXV) * sizeof(float)) + 1024));
         attr_set = true;
     }
     for (long long s0 = 0; s0 < N; s0 += chunk) {

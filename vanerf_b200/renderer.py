@@ -118,7 +118,13 @@ class Renderer:
         """TexVisFusion global feature per vertex, (V,1558,18) (src/networks.py:273-279).  LayerNorm shapes follow
         the actual map sizes."""
         sd = self.sd
+        # cuDNN would take TF32 for these convolutions by default (the reference's own GPU run does, SURVEY.md B-14);
+        # the CPU oracle is the arbiter, so the per-frame stacks run in true fp32.
+        with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True, allow_tf32=False):
+            return self._global_vertex_feature(img, feat_tex, sd)
 
+    @staticmethod
+    def _global_vertex_feature(img, feat_tex, sd):
         def stack(x, pre):
             x = F.conv2d(x, sd[pre + ".0.weight"], padding=1)
             x = F.relu(F.layer_norm(x, x.shape[-2:], sd[pre + ".1.weight"], sd[pre + ".1.bias"], 1e-6))
