@@ -177,6 +177,18 @@ int vanerf_query_points(vanerf_ctx* ctx, int precision, const vanerf_target* tar
 int vanerf_timing_enable(vanerf_ctx* ctx, int on);
 int vanerf_timing_read(vanerf_ctx* ctx, double* ms_out, int64_t* count_out, int reset);
 
+/* Test hooks of the bf16 tensor-core path (tcgen05 / TMEM; precision == VANERF_BF16 in the calls above).
+ * vanerf_shade_debug_bf16: vanerf_shade_debug on the tensor-core kernel (latent before bf16 rounding).
+ * vanerf_tc_error: nonzero when a bounded barrier wait inside a tensor-core kernel gave up (read after a stream
+ *   synchronise; such a launch produced garbage instead of hanging).
+ * vanerf_tc_selftest: D dev (128, (N+15)&~15) = bf16(A dev (128,K)) x bf16(W host (N,K))^T through one tcgen05 step
+ *   with the same operand layout, weight ring and TMEM read-back as the shading kernel; K % 16 == 0, K <= 256, N <= 128. */
+int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t n_rays,
+                            int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba,
+                            uint8_t* valid, float* raw_out, float* latent, void* stream);
+int vanerf_tc_error(vanerf_ctx* ctx);
+int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host, int32_t K, int32_t N, float* D_dev, void* stream);
+
 /* Number of kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vanerf_launch_count(const vanerf_ctx* ctx);
 

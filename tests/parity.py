@@ -19,6 +19,15 @@ TOL_FP32 = 1e-3
 TOL_BF16 = 1e-2
 
 
+def tol_for(precision, ref):
+    """fp32 path: 1e-3 max-abs.  bf16-MLP path: 1e-2 max-abs on outputs in the unit range (every reference-init case and
+    all colours a real model produces); the synthetic stress weights drive per-sample outputs up to |2.5|, where the
+    bar is 1e-2 of the output range."""
+    if precision == L.FP32:
+        return TOL_FP32
+    return TOL_BF16 * max(1.0, float(np.abs(np.asarray(ref)).max()))
+
+
 def lattice_pixels(H, W, npix):
     """Config-A style lattice of target pixels spread over the image."""
     ii, jj = np.meshgrid(np.arange(npix), np.arange(npix), indexing="ij")
@@ -73,7 +82,7 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
     orc = OT.Oracle(sd, inp)
     ot = {}
     oo = orc.render(fine=True, pixels=pixels, S_c=S_c, S_f=S_f, taps=ot)
-    errs = {}
+    errs = report if report is not None else {}
     # ---- per-frame visibility (bit-exact)
     assert_exact("vert_vis", _np(vert_vis), orc.frame["vert_vis"])
     tar = r.make_target(inp["cam_tar"], inp["bounds"])
@@ -98,10 +107,12 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
         rgba, valid, raw, lat = r.shade(tar, rays, z, geo, want_latent=True)
         errs["latent"] = assert_close("MLPUNetFusion latent", _np(lat), ot["query"]["latent"], tol)
     else:
-        rgba, valid, raw = r.shade(tar, rays, z, geo, precision=precision)
+        rgba, valid, raw, lat = r.shade(tar, rays, z, geo, precision=precision, want_latent=True)
+        errs["latent"] = assert_close("MLPUNetFusion latent (bf16 path)", _np(lat), ot["query"]["latent"], tol_for(precision, ot["query"]["latent"]))
     assert_exact("valid", _np(valid) > 0, ot["valid"])
-    errs["query_out"] = assert_close("VANeRF.query out", _np(raw), np.concatenate([ot["query"]["o"], ot["query"]["rgb"]], 1), tol)
-    errs["rgba"] = assert_close("rgba", _np(rgba), ot["rgba"], tol)
+    ref_raw = np.concatenate([ot["query"]["o"], ot["query"]["rgb"]], 1)
+    errs["query_out"] = assert_close("VANeRF.query out", _np(raw), ref_raw, tol_for(precision, ref_raw))
+    errs["rgba"] = assert_close("rgba", _np(rgba), ot["rgba"], tol_for(precision, ot["rgba"]))
     # ---- compositing given the oracle's rgba (isolates the kernel), then end to end
     dev = r.device
     comp_o = r.composite(torch.from_numpy(ot["rgba"]).to(dev), z, geo["sdf"].view(z.shape))
@@ -112,7 +123,7 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
                                    assert_close("composite alpha", _np(comp_o["alpha"]), ref_c["alpha"], 1e-5),
                                    assert_close("composite sdf", _np(comp_o["sdf"]), ref_c["sdf"], 1e-5))
     comp = r.composite(rgba, z, geo["sdf"].view(z.shape))
-    errs["tex_fg"] = assert_close("tex_fg", _np(comp["color"]), oo["tex_fg"], tol)
+    errs["tex_fg"] = assert_close("tex_fg", _np(comp["color"]), oo["tex_fg"], tol_for(precision, oo["tex_fg"]))
     errs["depth"] = assert_close("depth", _np(comp["depth"]), oo["depth"], tol)
     errs["alpha"] = assert_close("alpha", _np(comp["alpha"]), oo["alpha"], tol)
     # ---- importance sampling + merge given the oracle's contrib: bit-exact fine depths
@@ -127,12 +138,10 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
     assert_exact("fine query_vis", _np(geo2["qvis"]) > 0, ot["geo_fine"]["qvis"])
     rgba2, valid2, raw2 = r.shade(tar, rays, z2, geo2, precision=precision)
     assert_exact("fine valid", _np(valid2) > 0, ot["valid_fine"])
-    errs["rgba_fine"] = assert_close("rgba fine", _np(rgba2), ot["rgba_fine"], tol)
+    errs["rgba_fine"] = assert_close("rgba fine", _np(rgba2), ot["rgba_fine"], tol_for(precision, ot["rgba_fine"]))
     comp2 = r.composite(rgba2, z2, geo2["sdf"].view(z2.shape))
-    errs["tex_fg_fine"] = assert_close("tex_fg_fine", _np(comp2["color"]), oo["tex_fg_fine"], tol)
+    errs["tex_fg_fine"] = assert_close("tex_fg_fine", _np(comp2["color"]), oo["tex_fg_fine"], tol_for(precision, oo["tex_fg_fine"]))
     errs["sdf_fine"] = assert_close("sdf fine", _np(comp2["sdf"]), oo["sdf"], tol)
-    if report is not None:
-        report.update(errs)
     return errs, oo, ot
 
 
@@ -142,10 +151,11 @@ def check_render_rays(r: Renderer, inp, oo, pixels, precision=L.FP32, tol_fine=N
     tar = r.make_target(inp["cam_tar"], inp["bounds"])
     oc, of = r.render_rays(tar, torch.from_numpy(pixels), 64, 64, True, precision)
     oc, of = _np(oc), _np(of)
-    e = {"rr_tex_fg": assert_close("render_rays tex_fg", oc[:, :3], oo["tex_fg"], tol),
+    e = {"rr_tex_fg": assert_close("render_rays tex_fg", oc[:, :3], oo["tex_fg"], tol_for(precision, oo["tex_fg"])),
          "rr_depth": assert_close("render_rays depth", oc[:, 3], oo["depth"], tol),
          "rr_alpha": assert_close("render_rays alpha", oc[:, 4], oo["alpha"], tol)}
     # the fine pass re-samples from a cdf: its depths amplify fp rounding of contrib (reference vs its own CPU
     # restatement already differ by ~1e-3 on stress weights), hence the separate tolerance
-    e["rr_tex_fg_fine"] = assert_close("render_rays tex_fg_fine", of[:, :3], oo["tex_fg_fine"], tol_fine or tol)
+    e["rr_tex_fg_fine"] = assert_close("render_rays tex_fg_fine", of[:, :3], oo["tex_fg_fine"],
+                                       (tol_fine or tol) * (1.0 if precision == L.FP32 else max(1.0, float(np.abs(oo["tex_fg_fine"]).max()))))
     return e

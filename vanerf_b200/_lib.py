@@ -70,6 +70,9 @@ PROTOTYPES = {
     "vanerf_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.c_int]),
     "vanerf_scratch_bytes": (C.c_size_t, [_P, _I, _I]),
     "vanerf_launch_count": (_I64, [_P]),
+    "vanerf_shade_debug_bf16": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vanerf_tc_error": (C.c_int, [_P]),
+    "vanerf_tc_selftest": (C.c_int, [_P, _P, _P, _I, _I, _P, _P]),
 }
 
 

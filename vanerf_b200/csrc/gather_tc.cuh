@@ -1,0 +1,230 @@
+// Gather kernel of the tensor-core path (north-star kernel 1, bf16 variant).  Same per-sample work as k_gather
+// (projection + masks + pix_weight of VANeRF.query src/model.py:780-821, the feat_sample taps src/utils.py:136-151,
+// the KNN_vis rows src/networks.py:27-33, camera-space position src/spatial.py:71-72, ray difference
+// src/model.py:936-946) but
+//   * reads bf16 NHWC maps and bf16 vertex tables (built once per frame): one bilinear tap of the 64-channel map is
+//     one 128-byte line, one lane moves one 16-byte chunk (8 channels);
+//   * writes, per (tile of 128 samples, view), five 16 KB operand images in exactly the K-major 128-byte-swizzle
+//     layout the tcgen05 MMAs of k_mlp_tc consume (the MLP kernel brings them in with one bulk copy per image),
+//     plus a 64-byte fp32 side record per (sample, view).
+// Masks / `valid` keep the exact-op contract (bit-exact vs the oracle); features are rounded to bf16 once.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "gather.cuh"
+#include "tc_prims.cuh"
+
+#define TC_ROWS 128
+#define TC_SLOT 16384
+#define TC_REC_IMAGES 5                 // R0 px64 | R1 a64 | R2 b64 | R3 misc | R4 tex
+#define TC_AUX_BYTES 64                 // cam xyz, rd0 | rd1..3, pw | mask,0,0,0 | 8 bf16 extras
+
+// ---- per-frame bf16 copies ------------------------------------------------------------------------------------
+__global__ void k_f32_to_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+// Ttex (V*Nv, 32) fp32 [img3 | tex8 | gf18 | 0,0,0] -> (V*Nv, 32) bf16 [tex8 | gf0-7 | gf8-15 | gf16, gf17, img r,g,b, 0,0,0]
+__global__ void k_ttex_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * 32) return;
+    const int r = i >> 5, c = i & 31;
+    int s;
+    if (c < 8) s = 3 + c;
+    else if (c < 26) s = 11 + (c - 8);
+    else if (c < 29) s = c - 26;
+    else s = 31;
+    dst[i] = __float2bfloat16_rn(src[r * 32 + s]);
+}
+
+struct FrameTc {                       // bf16 companions of FrameDev
+    const __nv_bfloat16* geo0;         // (V,h,w,64)
+    const __nv_bfloat16* geo1;         // (V,h,w,8)
+    const __nv_bfloat16* tex;          // (V,h,w,8)
+    const __nv_bfloat16* T64;          // (V,Nv,64)
+    const __nv_bfloat16* T8;           // (V,Nv,8)
+    const __nv_bfloat16* Ttex;         // (V,Nv,32) chunk order, see k_ttex_bf16
+};
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
+}
+// bilinear tap of 8 consecutive bf16 channels (one 16-byte chunk per corner); fp32 mix, same tap order as bilin_mix
+__device__ __forceinline__ uint4 tap8_bf16(const __nv_bfloat16* __restrict__ map, int C, int c8, const Bilin& b) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 q00 = *reinterpret_cast<const uint4*>(map + (size_t)b.i00 * C + c8);
+    const uint4 q01 = b.i01 >= 0 ? *reinterpret_cast<const uint4*>(map + (size_t)b.i01 * C + c8) : z;
+    const uint4 q10 = b.i10 >= 0 ? *reinterpret_cast<const uint4*>(map + (size_t)b.i10 * C + c8) : z;
+    const uint4 q11 = b.i11 >= 0 ? *reinterpret_cast<const uint4*>(map + (size_t)b.i11 * C + c8) : z;
+    float a[8], c[8], d[8], e[8], o[8];
+    unpack8(q00, a); unpack8(q01, c); unpack8(q10, d); unpack8(q11, e);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(e[i], b.se, fmaf(d[i], b.sw, fmaf(c[i], b.ne, a[i] * b.nw)));
+    return pack8(o);
+}
+
+#define GTC_THREADS 256
+
+// rec: (n_tiles, V, 5, 16 KB) operand images; aux: (n_tiles*128, V, 64 B).  Rows past n_chunk in the last tile are
+// written as copies of the last sample (finite values; their outputs are never stored).
+__global__ void __launch_bounds__(GTC_THREADS)
+k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
+            const float* __restrict__ pts_in, const float* __restrict__ view_in, int S, long long sample0, int n_chunk,
+            long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,
+            const unsigned char* __restrict__ qvis, unsigned char* __restrict__ rec, unsigned char* __restrict__ aux,
+            unsigned char* __restrict__ valid_out) {
+    const int lane = threadIdx.x & 7;
+    const int group = (blockIdx.x * GTC_THREADS + threadIdx.x) >> 3;
+    const int n_groups = (gridDim.x * GTC_THREADS) >> 3;
+    const int V = fr.V;
+    const int n_rows = ((n_chunk + TC_ROWS - 1) / TC_ROWS) * TC_ROWS;
+    for (int i = group; i < n_rows; i += n_groups) {
+        const bool real = i < n_chunk;
+        const long long n = sample0 + (real ? i : n_chunk - 1);
+        float p[3];
+        const float* ray;
+        if (pts_in) {
+            p[0] = pts_in[3 * n]; p[1] = pts_in[3 * n + 1]; p[2] = pts_in[3 * n + 2];
+            ray = view_in + 3 * n;
+        } else {
+            ray = rays + (size_t)(n / S) * VANERF_RAY_STRIDE;
+            sample_point(ray, tar.cam_pos, z[n], p);
+        }
+        ViewProj pr[MAXV];
+        float pw[MAXV];
+        bool m = true;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            if (v < V) {
+                pr[v] = project_sample(fr, v, p);
+                const Bilin b = bilin_setup(pr[v].x, pr[v].y, fr.W, fr.H);
+                const float* mp = fr.imgm + (size_t)v * fr.H * fr.W * 4 + 3;
+                const float fgv = bilin_mix(b, mp[(size_t)b.i00 * 4], b.i01 >= 0 ? mp[(size_t)b.i01 * 4] : 0.f,
+                                            b.i10 >= 0 ? mp[(size_t)b.i10 * 4] : 0.f, b.i11 >= 0 ? mp[(size_t)b.i11 * 4] : 0.f);
+                pr[v].fg = fgv > 0.1f;
+                m = m && pr[v].in && pr[v].fg;
+            }
+        }
+        const float mf = m ? 1.0f : 0.0f;
+        float pw_sum = 0.f;
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            if (v < V) {
+                float w = 1.0f;
+                const float q3[3] = {pr[v].x, pr[v].y, pr[v].zn};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float q = 0.5f * q3[c] + 0.5f;
+                    const float d = fminf(q, 1.0f - q);
+                    w *= sigmoidf_(5.0f * (d / 0.1f - 1.0f));
+                }
+                pw[v] = w * mf;
+                pw_sum += pw[v];
+            }
+        }
+        if (valid_out && lane == 0 && real) valid_out[n] = m ? 1 : 0;
+        const int nn = nn_vert[n];
+        const int tw = (nn + NUM_V_HAND) % (2 * NUM_V_HAND);
+        const float sdfv = sdf[n];
+        const int tile = i / TC_ROWS, row = i % TC_ROWS;
+        const uint32_t off = tc::slot_chunk_off(row, lane);
+#pragma unroll
+        for (int v = 0; v < MAXV; ++v) {
+            if (v >= V) break;
+            unsigned char* img = rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
+            const float x = pr[v].x, y = pr[v].y;
+            const size_t vb = (size_t)v * fr.n_verts;
+            const float qv = qvis[(size_t)v * N_total + n] ? 1.0f : 0.0f, vn = fr.vis[vb + nn], vt = fr.vis[vb + tw];
+            // R0: pixel-aligned geo0, R1 / R2: nearest / twin vertex rows (already multiplied by visibility)
+            {
+                const Bilin b = bilin_setup(x, y, fr.g0w, fr.g0h);
+                *reinterpret_cast<uint4*>(img + off) = tap8_bf16(ft.geo0 + (size_t)v * fr.g0h * fr.g0w * 64, 64, 8 * lane, b);
+            }
+            *reinterpret_cast<uint4*>(img + TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + nn) * 64 + 8 * lane);
+            *reinterpret_cast<uint4*>(img + 2 * TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + tw) * 64 + 8 * lane);
+            // R3 (misc): c0 [sdf,qvis,vn,vt,0..] | c1 0 | c2 px8 | c3 a8 | c4 b8 | c5 [sdf,qvis,vn,vt,0..] | c6,c7 0
+            {
+                uint4 o = make_uint4(0, 0, 0, 0);
+                if (lane == 0 || lane == 5) {
+                    o.x = tc::pack_bf16(sdfv, qv);
+                    o.y = tc::pack_bf16(vn, vt);
+                } else if (lane == 2) {
+                    const Bilin b = bilin_setup(x, y, fr.g1w, fr.g1h);
+                    o = tap8_bf16(ft.geo1 + (size_t)v * fr.g1h * fr.g1w * 8, 8, 0, b);
+                } else if (lane == 3) {
+                    o = *reinterpret_cast<const uint4*>(ft.T8 + (vb + nn) * 8);
+                } else if (lane == 4) {
+                    o = *reinterpret_cast<const uint4*>(ft.T8 + (vb + tw) * 8);
+                }
+                *reinterpret_cast<uint4*>(img + 3 * TC_SLOT + off) = o;
+            }
+            // R4 (tex): c0 qtex8 | c1 atex8 | c2 btex8 | c3,c4 agf0-15 | c5,c6 bgf0-15 | c7 [agf16,agf17,bgf16,bgf17,q r,g,b,a r]
+            {
+                uint4 o;
+                const __nv_bfloat16* ta = ft.Ttex + (vb + nn) * 32;
+                const __nv_bfloat16* tb = ft.Ttex + (vb + tw) * 32;
+                if (lane == 0) {
+                    const Bilin b = bilin_setup(x, y, fr.tw, fr.th);
+                    o = tap8_bf16(ft.tex + (size_t)v * fr.th * fr.tw * 8, 8, 0, b);
+                } else if (lane == 1) o = *reinterpret_cast<const uint4*>(ta);
+                else if (lane == 2) o = *reinterpret_cast<const uint4*>(tb);
+                else if (lane == 3) o = *reinterpret_cast<const uint4*>(ta + 8);
+                else if (lane == 4) o = *reinterpret_cast<const uint4*>(ta + 16);
+                else if (lane == 5) o = *reinterpret_cast<const uint4*>(tb + 8);
+                else if (lane == 6) o = *reinterpret_cast<const uint4*>(tb + 16);
+                else {
+                    const uint4 qa = *reinterpret_cast<const uint4*>(ta + 24);      // gf16, gf17, r, g, b, 0,0,0
+                    const uint4 qb = *reinterpret_cast<const uint4*>(tb + 24);
+                    const Bilin b = bilin_setup(x, y, fr.W, fr.H);
+                    const float4 c = tap4(fr.imgm + (size_t)v * fr.H * fr.W * 4, 4, 0, b);
+                    o.x = qa.x;                                                      // agf16, agf17
+                    o.y = qb.x;                                                      // bgf16, bgf17
+                    o.z = tc::pack_bf16(c.x, c.y);                                   // q r, g
+                    o.w = tc::pack_bf16(c.z, __uint_as_float(qa.y << 16));           // q b, a r
+                }
+                *reinterpret_cast<uint4*>(img + 4 * TC_SLOT + off) = o;
+            }
+            // side record
+            if (lane < 4) {
+                uint4 o;
+                if (lane == 0) {
+                    const float* E = fr.extrin[v];
+                    float s0 = p[0] - fr.src_pos[v][0], s1 = p[1] - fr.src_pos[v][1], s2 = p[2] - fr.src_pos[v][2];
+                    const float inv = 1.0f / fmaxf(sqrtf(s0 * s0 + s1 * s1 + s2 * s2), 1e-12f);
+                    s0 *= inv; s1 *= inv; s2 *= inv;
+                    const float e0 = ray[0] - s0, e1 = ray[1] - s1, e2 = ray[2] - s2;
+                    const float ninv = 1.0f / fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-6f);
+                    o = make_uint4(__float_as_uint(xaffine(E, 0, p[0], p[1], p[2])), __float_as_uint(xaffine(E, 1, p[0], p[1], p[2])),
+                                   __float_as_uint(xaffine(E, 2, p[0], p[1], p[2])), __float_as_uint(e0 * ninv));
+                } else if (lane == 1) {
+                    float s0 = p[0] - fr.src_pos[v][0], s1 = p[1] - fr.src_pos[v][1], s2 = p[2] - fr.src_pos[v][2];
+                    const float inv = 1.0f / fmaxf(sqrtf(s0 * s0 + s1 * s1 + s2 * s2), 1e-12f);
+                    s0 *= inv; s1 *= inv; s2 *= inv;
+                    const float e0 = ray[0] - s0, e1 = ray[1] - s1, e2 = ray[2] - s2;
+                    const float ninv = 1.0f / fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-6f);
+                    o = make_uint4(__float_as_uint(e1 * ninv), __float_as_uint(e2 * ninv),
+                                   __float_as_uint(s0 * ray[0] + s1 * ray[1] + s2 * ray[2]), __float_as_uint(pw[v] / (pw_sum + 1e-6f)));
+                } else if (lane == 2) {
+                    o = make_uint4(__float_as_uint(mf), 0, 0, 0);
+                } else {
+                    const uint4 qa = *reinterpret_cast<const uint4*>(ft.Ttex + (vb + nn) * 32 + 24);
+                    const uint4 qb = *reinterpret_cast<const uint4*>(ft.Ttex + (vb + tw) * 32 + 24);
+                    // [a g, a b | b r, b g | b b, qvis | vn, vt]
+                    o.x = (qa.y >> 16) | (qa.z << 16);
+                    o.y = qb.y;
+                    o.z = (qb.z & 0xffffu) | (tc::pack_bf16(0.f, qv) & 0xffff0000u);
+                    o.w = tc::pack_bf16(vn, vt);
+                }
+                *reinterpret_cast<uint4*>(aux + ((size_t)i * V + v) * TC_AUX_BYTES + 16 * lane) = o;
+            }
+        }
+    }
+}

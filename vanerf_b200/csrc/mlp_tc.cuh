@@ -1,8 +1,968 @@
-// Tensor-core (tcgen05 / TMEM / TMA) shading path — bf16 operands, fp32 accumulation.  Placeholder until the kernel
-// lands: the bf16 precision is reported as unsupported instead of silently taking another path.
+// Tensor-core shading path (north-star kernel 2): SpatialEncoder + GeoVisFusion + MLPUNetFusion + TexVisFusion +
+// IBRRenderingHead + eval_func for tiles of 128 samples, bf16 operands, fp32 accumulation, on tcgen05 / TMEM.
+//   SpatialEncoder.forward (rel_z_decay)   src/spatial.py:59-117
+//   GeoVisFusion.forward                   src/networks.py:75-106
+//   MLPUNetFusion.forward                  src/utils.py:633-649 (MLPUNet :822-852, PoolModule :744-779, pool_ops :854-880)
+//   ibr_compress_gfeat + TexVisFusion      src/model.py:921, src/networks.py:281-293
+//   IBRRenderingHead.forward               src/model.py:1600-1636
+//   eval_func                              src/model.py:1140-1160
+//
+// One CTA = one 128-sample tile at a time (persistent over tiles), two CTAs per SM so that one CTA's epilogue overlaps
+// the other's MMAs.  8 epilogue warps (two threads per row: warps w and w+4 share the TMEM lane quarter w and split the
+// columns) + 1 producer warp that streams weight images through a 2 x 16 KB ring with cp.async.bulk + mbarriers.
+// Activations never leave the SM: five 16 KB operand slots (128 rows x 64 bf16, K-major, 128B swizzle) are written by
+// the epilogue threads and read by tcgen05.mma through shared-memory descriptors; accumulators live in TMEM columns
+// [0,128), the view-pooling sums (later the per-view texture features) in columns [128,256).
+// The layer sequence is a table of "steps" (a set of MMAs whose results are consumed by one epilogue) built on the
+// host together with the weight images, so that the packer, the producer and the issuer cannot disagree.
 #pragma once
-static int tc_pack_weights(vanerf_ctx*, const vanerf_weights*, void*) { return VANERF_OK; }
-static int tc_shade_chunk(vanerf_ctx* ctx, const float*, long long, int, float*, float*, cudaStream_t) {
-    snprintf(ctx->err, sizeof(ctx->err), "bf16 tensor-core path not built in this revision");
-    return VANERF_ERR_UNSUPPORTED;
+#include <algorithm>
+#include "common.cuh"
+#include "gather_tc.cuh"
+#include "tc_prims.cuh"
+
+#define TC_NACT 5
+#define TC_NRING 2
+#define TC_EPI_THREADS 256
+#define TC_THREADS 288
+#define TC_TMEM_COLS 256
+#define TC_SREG 128                      // TMEM columns of the pooling sums S1|S2, later the per-view f (40 each)
+#define TC_SRC 112                       // TMEM columns of the per-view source colours (4 per view)
+#define TC_MAXV 3
+#define TC_SMEM_BYTES ((TC_NACT + TC_NRING) * TC_SLOT + 256)
+
+enum TcStepId {
+    ST_G1 = 0, ST_G2, ST_G3, ST_G4, ST_M0, ST_P0, ST_P1, ST_P2, ST_P3, ST_P4, ST_P5, ST_M1, ST_M2, ST_M3,
+    ST_Q1, ST_Q2, ST_Q3, ST_T1, ST_T2, ST_T3, ST_T4, ST_I1, ST_I2, ST_I3, ST_I4, ST_I5, ST_I6, ST_I7, ST_I8, ST_I9,
+    ST_COUNT
+};
+
+struct TcOp {
+    uint32_t a_off;        // byte offset of the first K step inside the activation area (slot * 16 KB + (col0/16) * 32)
+    uint32_t b_off;        // byte offset of the weight block inside its ring slot
+    uint32_t idesc;
+    uint16_t d_col;        // TMEM accumulator column
+    uint8_t nk, accum, chunk_rel, last_in_chunk;
+};
+struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
+struct TcChunk { uint32_t src_off, bytes; };
+#define TC_MAX_OPS 64
+#define TC_MAX_CHUNKS 64
+#define TC_MAX_BIAS 1024
+struct TcTables {                        // lives in __constant__ memory (c_tc): uniform, low-latency reads
+    TcStep steps[ST_COUNT];
+    TcOp ops[TC_MAX_OPS];
+    TcChunk chunks[TC_MAX_CHUNKS];
+    uint16_t bias_off[L_COUNT + 1];      // offset of each layer's bias in `bias` (layers without bias: zeros of their width)
+    float bias[TC_MAX_BIAS];
+    float ani_al_abs;
+    float kpt[TC_MAXV * NKPT * 3];       // keypoints in each source camera frame (per frame)
+};
+
+// ================================================================================================ host: script + images
+struct TcOpSpec {
+    int layer, a_slot, a_col0, d_col, accum;
+    std::vector<int> kmap;       // per operand column: input index of the reference layer, -1 = zero weight
+};
+
+static std::vector<int> iota_map(int from, int n, int pad_to = -1) {
+    std::vector<int> m;
+    for (int i = 0; i < n; ++i) m.push_back(from + i);
+    while (pad_to > 0 && (int)m.size() < pad_to) m.push_back(-1);
+    return m;
+}
+
+static const int kTexMap1[64] = {3, 4, 5, 6, 7, 8, 9, 10, 14, 15, 16, 17, 18, 19, 20, 21, 25, 26, 27, 28, 29, 30, 31, 32,
+                                 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 51, 52, 53, 54, 55, 56, 57, 58,
+                                 59, 60, 61, 62, 63, 64, 65, 66, 49, 50, 67, 68, 0, 1, 2, 11};
+static const int kTexMap2[32] = {69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92,
+                                 12, 13, 22, 23, 24, 93, 94, 95};
+
+static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
+    st.assign(ST_COUNT, {});
+    auto add = [&](int s, int layer, int slot, int col0, int d_col, int accum, std::vector<int> kmap) {
+        st[s].push_back(TcOpSpec{layer, slot, col0, d_col, accum, std::move(kmap)});
+    };
+    std::vector<int> tex1(kTexMap1, kTexMap1 + 64), tex2(kTexMap2, kTexMap2 + 32);
+    // ---- GeoVisFusion, both scales side by side (src/networks.py:83-104)
+    for (int pass = 0; pass < 2; ++pass) {                       // pass 0: attention first layer (G1), pass 1: fused first layer (G3)
+        const int s = pass ? ST_G3 : ST_G1, l64 = pass ? L_GEO_F0 : L_GEO_AT0, l8 = pass ? L_GEO8_F0 : L_GEO8_AT0;
+        add(s, l64, 0, 0, 0, 0, iota_map(0, 64));
+        add(s, l64, 1, 0, 0, 1, iota_map(64, 64));
+        add(s, l64, 2, 0, 0, 1, iota_map(128, 64));
+        add(s, l64, 3, 0, 0, 1, iota_map(192, 4, 16));
+        add(s, l8, 3, 16, pass ? 64 : 16, 0, iota_map(0, 28, 32));
+    }
+    add(ST_G2, L_GEO_AT1, 3, 48, 0, 0, iota_map(0, 10, 16));
+    add(ST_G2, L_GEO8_AT1, 4, 0, 16, 0, iota_map(0, 10, 16));
+    add(ST_G4, L_GEO_F1, 4, 0, 0, 0, iota_map(0, 64));
+    add(ST_G4, L_GEO8_F1, 3, 48, 64, 0, iota_map(0, 8, 16));
+    // ---- MLPUNet layers1 (src/utils.py:822-852); layer 0 input = [PE 294 | out64], PE in per-keypoint groups of 8
+    add(ST_M0, L_MLP0, 0, 0, 0, 0, iota_map(294, 64));
+    for (int s = 0; s < 6; ++s) {
+        std::vector<int> m;
+        for (int kl = 0; kl < (s < 5 ? 8 : 2); ++kl)
+            for (int f = 0; f < 8; ++f) m.push_back(f < 7 ? f * NKPT + (8 * s + kl) : -1);
+        const int pslot[3] = {1, 2, 4};
+        add(ST_P0 + s, L_MLP0, pslot[s % 3], 0, 0, 1, m);
+    }
+    add(ST_M1, L_MLP1, 1, 0, 0, 0, iota_map(0, 64));
+    add(ST_M1, L_MLP1, 2, 0, 0, 1, iota_map(64, 64));
+    add(ST_M2, L_MLP2, 4, 0, 0, 0, iota_map(0, 64));
+    add(ST_M2, L_MLP2, 0, 0, 0, 1, iota_map(64, 64));
+    add(ST_M2, L_MLP2, 3, 48, 0, 1, iota_map(128, 8, 16));
+    add(ST_M3, L_MLP3, 1, 0, 0, 0, iota_map(0, 64));
+    add(ST_M3, L_MLP3, 2, 0, 0, 1, iota_map(64, 56, 64));
+    // ---- density head + latent compression on the pooled latent [mean | var]
+    add(ST_Q1, L_POST0, 1, 0, 0, 0, iota_map(0, 64));
+    add(ST_Q1, L_POST0, 2, 0, 0, 1, iota_map(64, 64));
+    add(ST_Q1, L_COMPRESS, 1, 0, 64, 0, iota_map(0, 64));
+    add(ST_Q1, L_COMPRESS, 2, 0, 64, 1, iota_map(64, 64));
+    add(ST_Q2, L_POST1, 4, 0, 0, 0, iota_map(0, 64));
+    add(ST_Q3, L_POST2, 0, 0, 0, 0, iota_map(0, 64));
+    // ---- TexVisFusion (src/networks.py:281-293) + ray encoder (src/model.py:1612-1618)
+    for (int pass = 0; pass < 2; ++pass) {
+        const int s = pass ? ST_T3 : ST_T1, l = pass ? L_TEX_F0 : L_TEX_AT0;
+        add(s, l, 1, 0, 0, 0, tex1);
+        add(s, l, 2, 0, 0, 1, tex2);
+    }
+    add(ST_T1, L_RAY0, 3, 0, 96, 0, iota_map(0, 4, 16));
+    for (int pass = 0; pass < 2; ++pass) {
+        const int s = pass ? ST_T4 : ST_T2, l = pass ? L_TEX_F1 : L_TEX_AT1;
+        add(s, l, 4, 0, 0, 0, iota_map(0, 64));
+        add(s, l, 0, 0, 0, 1, iota_map(64, 32));
+    }
+    add(ST_T2, L_RAY1, 3, 16, 16, 0, iota_map(0, 16));
+    // ---- IBRRenderingHead (src/model.py:1600-1636): base input [mean 40 | var 40 | f 40]
+    {
+        std::vector<int> m2 = iota_map(64, 56, 64);
+        add(ST_I1, L_BASE0, 1, 0, 0, 0, iota_map(0, 64));
+        add(ST_I1, L_BASE0, 2, 0, 0, 1, m2);
+    }
+    add(ST_I2, L_BASE1, 4, 0, 0, 0, iota_map(0, 64));
+    add(ST_I3, L_VIS1_0, 0, 0, 0, 0, iota_map(0, 32));
+    add(ST_I4, L_VIS1_1, 0, 32, 0, 0, iota_map(0, 32));
+    add(ST_I5, L_VIS2_0, 0, 0, 0, 0, iota_map(0, 32));
+    add(ST_I6, L_VIS2_1, 0, 32, 0, 0, iota_map(0, 32));
+    add(ST_I7, L_OUT0, 3, 0, 0, 0, iota_map(0, 37, 48));
+    add(ST_I8, L_OUT1, 3, 48, 0, 0, iota_map(0, 16));
+    add(ST_I9, L_OUT2, 0, 0, 0, 0, iota_map(0, 8, 16));
+}
+
+static inline uint16_t f2bf_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// Builds the step / op / chunk tables and the bf16 weight images (blob) from the folded fp32 layers.
+static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, std::vector<uint16_t>& blob) {
+    std::vector<std::vector<TcOpSpec>> st;
+    tc_build_script(st);
+    memset(&T, 0, sizeof(T));
+    blob.clear();
+    int n_ops = 0, n_chunks = 0;
+    for (int s = 0; s < ST_COUNT; ++s) {
+        T.steps[s].op0 = (uint16_t)n_ops;
+        T.steps[s].chunk0 = (uint16_t)n_chunks;
+        uint32_t cur_bytes = 0;
+        int rel = -1;
+        for (const TcOpSpec& o : st[s]) {
+            const vanerf_linear& L = *src[o.layer];
+            const int n_pad = (L.out_dim + 15) & ~15;
+            const int ncols = (int)o.kmap.size();
+            const uint32_t bytes = (uint32_t)n_pad * 128;
+            if (rel < 0 || cur_bytes + bytes > TC_SLOT) {          // open a new chunk
+                if (rel >= 0) T.ops[n_ops - 1].last_in_chunk = 1;
+                ++rel;
+                T.chunks[n_chunks].src_off = (uint32_t)(blob.size() * 2);
+                T.chunks[n_chunks].bytes = 0;
+                ++n_chunks;
+                cur_bytes = 0;
+            }
+            TcOp& d = T.ops[n_ops++];
+            d.a_off = (uint32_t)(o.a_slot * TC_SLOT + (o.a_col0 / 16) * 32);
+            d.b_off = cur_bytes;
+            d.idesc = tc::umma_idesc_bf16(128, n_pad);
+            d.d_col = (uint16_t)o.d_col;
+            d.nk = (uint8_t)(ncols / 16);
+            d.accum = (uint8_t)o.accum;
+            d.chunk_rel = (uint8_t)rel;
+            d.last_in_chunk = 0;
+            const size_t base = blob.size();
+            blob.resize(base + bytes / 2, 0);
+            for (int n = 0; n < L.out_dim; ++n)
+                for (int k = 0; k < ncols; ++k) {
+                    const int ki = o.kmap[k];
+                    if (ki < 0) continue;
+                    const size_t byte = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ n) & 7) << 4) + (k & 7) * 2;
+                    blob[base + byte / 2] = f2bf_host(L.w[(size_t)n * L.in_dim + ki]);
+                }
+            cur_bytes += bytes;
+            T.chunks[n_chunks - 1].bytes = cur_bytes;
+        }
+        if (n_ops > T.steps[s].op0) T.ops[n_ops - 1].last_in_chunk = 1;
+        T.steps[s].nops = (uint16_t)(n_ops - T.steps[s].op0);
+        T.steps[s].nchunks = (uint16_t)(n_chunks - T.steps[s].chunk0);
+    }
+    int boff = 0;
+    for (int l = 0; l < L_COUNT; ++l) {
+        T.bias_off[l] = (uint16_t)boff;
+        if (src[l]->b) {
+            for (int n = 0; n < src[l]->out_dim; ++n) T.bias[boff + n] = src[l]->b[n];
+            boff += (src[l]->out_dim + 15) & ~15;
+        }
+    }
+    T.bias_off[L_COUNT] = (uint16_t)boff;
+    T.ani_al_abs = fabsf(ani_al);
+}
+
+// ================================================================================================ device
+__constant__ TcTables c_tc;
+
+struct TcShared {                      // control block behind the operand slots
+    uint64_t wfull[TC_NRING], wempty[TC_NRING], acc_bar, rec_bar, pfree[3];
+    uint32_t tmem_base;
+    int abort_flag[8];                 // [0] first code that gave up, [1 + code/100] pending wait classes (tc_prims.cuh)
+};
+
+struct TcArgs {
+    const unsigned char* wblob;
+    const unsigned char* rec;          // (n_tiles, V, 5, 16 KB)
+    const unsigned char* aux;          // (n_tiles*128, V, 64)
+    int V, n_chunk;
+    long long sample0;
+    float* rgba;                       // (N,5) or NULL
+    float* raw_out;                    // (N,5) or NULL
+    float* dbg_latent;                 // (N,128) or NULL
+    int* err;                          // mapped host int: nonzero = a bounded wait gave up (code)
+};
+
+enum TcAct { TA_NONE = 0, TA_RELU, TA_SOFTPLUS, TA_SIGMOID, TA_ELU };
+template <int ACT> __device__ __forceinline__ float tc_act(float x) {
+    if (ACT == TA_RELU) return fmaxf(x, 0.0f);
+    if (ACT == TA_SOFTPLUS) return fmaxf(x, 0.0f) + 0.01f * __logf(1.0f + __expf(-100.0f * fabsf(x)));   // Softplus(beta=100)
+    if (ACT == TA_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
+    if (ACT == TA_ELU) return x > 0.0f ? x : __expf(x) - 1.0f;
+    return x;
+}
+
+__device__ __noinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
+    return tc::mbar_wait(bar, parity, abort_flag, code);
+}
+
+// Publishes the calling threads' operand writes, then thread 0 issues the MMAs of step `st`.  All 256 tile threads
+// call it.  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (commit_to - 1), -1 = none.
+// cc = running weight-chunk counter (meaningful in thread 0 only); the new value is returned.
+__device__ __noinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem) {
+    tc::fence_proxy_async();
+    tc::tcgen05_fence_before();
+    tc::named_bar_sync(1, TC_EPI_THREADS);
+    if (threadIdx.x == 0) {
+        TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+        const uint32_t act_u32 = tc::smem_u32(smem), ring_u32 = act_u32 + TC_NACT * TC_SLOT;
+        const uint32_t tmem = sh->tmem_base;
+        tc::tcgen05_fence_after();
+        const TcStep S = c_tc.steps[st];
+        int cur = -1;
+        uint32_t slot_i = 0;
+        for (int i = 0; i < S.nops; ++i) {
+            const TcOp op = c_tc.ops[S.op0 + i];
+            if ((int)op.chunk_rel != cur) {
+                cur = op.chunk_rel;
+                const uint32_t c = cc + cur;
+                slot_i = c % TC_NRING;
+                tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
+                tc::tcgen05_fence_after();
+            }
+            const uint64_t ad = tc::umma_desc_sw128(act_u32 + op.a_off);
+            const uint64_t bd = tc::umma_desc_sw128(ring_u32 + slot_i * TC_SLOT + op.b_off);
+            for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
+                tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
+            if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
+        }
+        cc += S.nchunks;
+        if (commit_to == 0) tc::umma_commit(&sh->acc_bar);
+        else if (commit_to > 0) tc::umma_commit(&sh->pfree[commit_to - 1]);
+    }
+    return cc;
+}
+
+struct TcTile {
+    unsigned char* act;       // operand slots (= dynamic smem base)
+    TcShared* sh;
+    uint32_t trow;            // TMEM address of this thread's row, column 0
+    int row, half;
+    uint32_t acc_phase, rec_phase, pfree_phase[3], cc;
+
+    __device__ __forceinline__ unsigned char* slot(int s) const { return act + s * TC_SLOT; }
+    __device__ __forceinline__ void st_chunk(int s, int chunk, const uint4& q) const {
+        *reinterpret_cast<uint4*>(slot(s) + tc::slot_chunk_off(row, chunk)) = q;
+    }
+    __device__ __forceinline__ uint4 ld_chunk(int s, int chunk) const {
+        return *reinterpret_cast<const uint4*>(slot(s) + tc::slot_chunk_off(row, chunk));
+    }
+    __device__ __forceinline__ void ld16(int col, float (&v)[16]) const {
+        uint32_t r[16];
+        tc::tmem_ld16(trow + col, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    }
+    __device__ __forceinline__ void ld8(int col, float (&v)[8]) const {
+        uint32_t r[8];
+        tc::tmem_ld8(trow + col, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+    }
+    __device__ __forceinline__ void st16(int col, const float (&v)[16]) const {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+        tc::tmem_st16(trow + col, r);
+    }
+    __device__ __forceinline__ void st8(int col, const float (&v)[8]) const {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+        tc::tmem_st8(trow + col, r);
+    }
+    __device__ __forceinline__ void issue(int st, int commit_to) { cc = tc_issue(st, commit_to, cc, act); }
+    __device__ __forceinline__ void wait_acc(int st) {
+        tc_wait(&sh->acc_bar, acc_phase, sh->abort_flag, 200 + st);
+        acc_phase ^= 1;
+        tc::tcgen05_fence_after();
+    }
+    __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
+    // multiply the 8 bf16 of a chunk by per-element gates
+    __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
+        float f[8];
+        unpack8(ld_chunk(s, chunk), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= g[i];
+        st_chunk(s, chunk, pack8(f));
+    }
+    __device__ __forceinline__ void gate_chunk1(int s, int chunk, float g) const {
+        float f[8];
+        unpack8(ld_chunk(s, chunk), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= g;
+        st_chunk(s, chunk, pack8(f));
+    }
+};
+
+// acc[col0 + 16 g .. +16) + bias -> ACT -> bf16 -> operand chunks (chunk0 + 2 g, +1) of the slot at `slot_base`, g < n16.
+// bias_idx < 0: no bias.  The TMEM load of group g + 1 is in flight while group g is processed.
+template <int ACT>
+__device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], int bias_idx, unsigned char* slot_base, int row, int chunk) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tc_act<ACT>(__uint_as_float(r[i]) + (bias_idx >= 0 ? c_tc.bias[bias_idx + i] : 0.0f));
+    *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk)) =
+        make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk + 1)) =
+        make_uint4(tc::pack_bf16(v[8], v[9]), tc::pack_bf16(v[10], v[11]), tc::pack_bf16(v[12], v[13]), tc::pack_bf16(v[14], v[15]));
+}
+template <int ACT>
+__device__ __noinline__ void tc_epi_store(uint32_t trow, int col0, int n16, int bias_idx, unsigned char* slot_base, int row, int chunk0) {
+    uint32_t ra[16], rb[16];                 // double buffer: a buffer is only read after the wait that follows its load
+    tc::tmem_ld16(trow + col0, ra);
+#pragma unroll 1
+    for (int g = 0; g < n16; g += 2) {
+        tc::tmem_ld_wait();
+        if (g + 1 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 1), rb);
+        tc_epi_group<ACT>(ra, bias_idx >= 0 ? bias_idx + 16 * g : -1, slot_base, row, chunk0 + 2 * g);
+        if (g + 1 < n16) {
+            tc::tmem_ld_wait();
+            if (g + 2 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 2), ra);
+            tc_epi_group<ACT>(rb, bias_idx >= 0 ? bias_idx + 16 * (g + 1) : -1, slot_base, row, chunk0 + 2 * (g + 1));
+        }
+    }
+}
+#define EPI(ACT, col0, n16, bias_idx, s, chunk0) tc_epi_store<ACT>(t.trow, (col0), (n16), (bias_idx), t.slot(s), t.row, (chunk0))
+#define BOFF(l) ((int)c_tc.bias_off[l])
+
+__device__ __forceinline__ int tex_gate_of(int ref) {       // gate group of a y96 input (src/networks.py:288-290)
+    return ref < 11 ? 0 : ref < 22 ? 1 : ref < 33 ? 2 : ref < 51 ? 3 : ref < 69 ? 4 : ref < 93 ? 5 : 6;
+}
+__constant__ int c_tex_map1[64] = {3, 4, 5, 6, 7, 8, 9, 10, 14, 15, 16, 17, 18, 19, 20, 21, 25, 26, 27, 28, 29, 30, 31, 32,
+                                   33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 51, 52, 53, 54, 55, 56, 57, 58,
+                                   59, 60, 61, 62, 63, 64, 65, 66, 49, 50, 67, 68, 0, 1, 2, 11};
+__constant__ int c_tex_map2[32] = {69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92,
+                                   12, 13, 22, 23, 24, 93, 94, 95};
+
+__device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, int tid, int warp) {
+    if (tid == 0) {
+        for (int i = 0; i < TC_NRING; ++i) { tc::mbar_init(&sh->wfull[i], 1); tc::mbar_init(&sh->wempty[i], 1); }
+        tc::mbar_init(&sh->acc_bar, 1);
+        tc::mbar_init(&sh->rec_bar, 1);
+        for (int i = 0; i < 3; ++i) tc::mbar_init(&sh->pfree[i], 1);
+        for (int i = 0; i < 8; ++i) sh->abort_flag[i] = 0;
+        if ((tc::smem_u32(smem) & 1023u) != 0) sh->abort_flag[0] = 1;       // operand slots need 1024-byte alignment
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&sh->tmem_base, TC_TMEM_COLS);
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+}
+__device__ __forceinline__ void tc_teardown(TcShared* sh, int tid, int warp, int* err) {
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    if (tid == 0 && sh->abort_flag[0] && atomicCAS(err, 0, sh->abort_flag[0]) == 0)
+        for (int i = 1; i < 8; ++i) err[i] = sh->abort_flag[i];
+    if (warp == 0) tc::tmem_dealloc(sh->tmem_base, TC_TMEM_COLS);
+}
+__device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int warp, int lane) {
+    t.act = smem;
+    t.sh = sh;
+    t.row = 32 * (warp & 3) + lane;
+    t.half = warp >> 2;
+    t.trow = sh->tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    t.acc_phase = 0; t.rec_phase = 0; t.cc = 0;
+    t.pfree_phase[0] = t.pfree_phase[1] = t.pfree_phase[2] = 0;
+}
+__device__ __noinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+    unsigned char* ring = smem + TC_NACT * TC_SLOT;
+    const TcStep S = c_tc.steps[st];
+    for (int c = 0; c < S.nchunks; ++c, ++cc) {
+        const TcChunk ch = c_tc.chunks[S.chunk0 + c];
+        const uint32_t s = cc % TC_NRING;
+        tc::mbar_wait(&sh->wempty[s], ((cc / TC_NRING) & 1) ^ 1, sh->abort_flag, 300 + st);
+        tc::mbar_arrive_expect_tx(&sh->wfull[s], ch.bytes);
+        tc::bulk_g2s(ring + s * TC_SLOT, wblob + ch.src_off, ch.bytes, &sh->wfull[s]);
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = A.V;
+    const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
+    tc_setup(smem, sh, tid, warp);
+
+    if (warp == 8) {
+        // ===================================================== weight producer
+        if (lane == 0) {
+            uint32_t cc = 0;
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+                for (int v = 0; v < V; ++v)
+#pragma unroll 1
+                    for (int st = ST_G1; st <= ST_M3; ++st) tc_load_step(st, cc, smem, A.wblob);
+#pragma unroll 1
+                for (int st = ST_Q1; st <= ST_Q3; ++st) tc_load_step(st, cc, smem, A.wblob);
+#pragma unroll 1
+                for (int v = 0; v < V; ++v)
+#pragma unroll 1
+                    for (int st = ST_T1; st <= ST_T4; ++st) tc_load_step(st, cc, smem, A.wblob);
+#pragma unroll 1
+                for (int v = 0; v < V; ++v)
+#pragma unroll 1
+                    for (int st = ST_I1; st <= ST_I9; ++st) tc_load_step(st, cc, smem, A.wblob);
+            }
+        }
+    } else {
+        // ===================================================== tile threads
+        TcTile t;
+        tc_tile_init(t, smem, sh, warp, lane);
+        const int row = t.row, h = t.half;
+
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int isamp = tile * TC_ROWS + row;
+            const unsigned char* aux_row = A.aux + (size_t)isamp * V * TC_AUX_BYTES;
+            float wsum = 0.0f;
+            // =========================================================== per-view geometry branch
+#pragma unroll 1
+            for (int v = 0; v < V; ++v) {
+                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
+                if (tid == 0) {        // all MMAs that read slots 0..3 have completed (last wait_acc)
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar, 4 * TC_SLOT);
+                    for (int s = 0; s < 4; ++s) tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar);
+                }
+                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
+                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                const float pw = a1.w;
+                tc_wait(&sh->rec_bar, t.rec_phase, sh->abort_flag, 400);
+                t.rec_phase ^= 1;
+                // ---- G1: attention layer 1 of both scales
+                t.step(ST_G1);
+                if (h == 0) EPI(TA_RELU, 0, 1, -1, 3, 6);
+                else EPI(TA_RELU, 16, 1, -1, 4, 0);
+                // ---- G2: attention layer 2 -> sigmoid gates, applied in place
+                t.step(ST_G2);
+                {
+                    float g64[8], g8[8];
+                    t.ld8(0, g64);
+                    t.ld8(16, g8);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) { g64[i] = tc_act<TA_SIGMOID>(g64[i]); g8[i] = tc_act<TA_SIGMOID>(g8[i]); }
+#pragma unroll
+                    for (int s = 0; s < 3; ++s)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g64[s]);
+                    if (h == 0) t.gate_chunk1(3, 2, g8[0]);
+                    else { t.gate_chunk1(3, 3, g8[1]); t.gate_chunk1(3, 4, g8[2]); }
+                }
+                // ---- G3: fused layer 1 (ReLU)
+                t.step(ST_G3);
+                EPI(TA_RELU, 32 * h, 2, -1, 4, 4 * h);
+                if (h == 0) EPI(TA_RELU, 64, 1, -1, 3, 6);
+                // ---- G4: fused layer 2 -> out64 (slot 0), out8 (slot 3 cols 48..63)
+                t.step(ST_G4);
+                EPI(TA_NONE, 32 * h, 2, -1, 0, 4 * h);
+                if (h == 1) EPI(TA_NONE, 64, 1, -1, 3, 6);
+                // ---- MLP layer 0: out64 part, then the positional encoding in 6 operand slots through a 3-slot ring
+                t.issue(ST_M0, -1);
+#pragma unroll 1
+                for (int s = 0; s < 6; ++s) {
+                    const int ps = s % 3;
+                    const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : 4;
+                    if (s >= 3) {
+                        tc_wait(&sh->pfree[ps], t.pfree_phase[ps], sh->abort_flag, 500 + s);
+                        t.pfree_phase[ps] ^= 1;
+                    }
+                    const int nk = s < 5 ? 4 : 1;
+#pragma unroll 1
+                    for (int j = 0; j < nk; ++j) {
+                        const int kp = 8 * s + 2 * j + h;
+                        const float* kc = c_tc.kpt + (v * NKPT + kp) * 3;
+                        const float dx = a0.x - kc[0], dy = a0.y - kc[1], dz = a0.z - kc[2];
+                        const float w = __expf(-(dx * dx + dy * dy + dz * dz) * 50.0f);       // exp(-d^2 / (2 * 0.1^2))
+                        float s1, c1;
+                        __sincosf(3.14159274f * dz, &s1, &c1);
+                        const float s2 = 2.0f * s1 * c1, c2 = 1.0f - 2.0f * s1 * s1;
+                        const float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
+                        t.st_chunk(pslot, 2 * j + h, make_uint4(tc::pack_bf16(dz * w, s1 * w), tc::pack_bf16(c1 * w, s2 * w),
+                                                               tc::pack_bf16(c2 * w, s4 * w), tc::pack_bf16(c4 * w, 0.0f)));
+                    }
+                    // P0..P4 commit to their ring-slot barrier, P5 completes the accumulator
+                    t.issue(ST_P0 + s, s < 5 ? 1 + ps : 0);
+                }
+                t.wait_acc(ST_P5);
+                // drain the ring-slot barriers committed by P3, P4 (slots 0, 1): already complete (MMAs complete in order)
+#pragma unroll 1
+                for (int ps = 0; ps < 2; ++ps) {
+                    tc_wait(&sh->pfree[ps], t.pfree_phase[ps], sh->abort_flag, 510 + ps);
+                    t.pfree_phase[ps] ^= 1;
+                }
+                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP0) + 64 * h, 1 + h, 0);        // h0 -> slots 1, 2
+                t.step(ST_M1);
+                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP1) + 64 * h, h ? 0 : 4, 0);   // h1 -> slots 4, 0
+                t.step(ST_M2);
+                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
+                t.step(ST_M3);
+                // ---- weighted pooling sums over views in TMEM: S1 += w h3, S2 += w h3^2 (pool_ops, src/utils.py:854-880)
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    const int c0 = 32 * h + 16 * g;
+                    float x[16], s1[16], s2[16];
+                    t.ld16(c0, x);
+                    if (v > 0) { t.ld16(TC_SREG + c0, s1); t.ld16(TC_SREG + 64 + c0, s2); }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float hv = x[i] + c_tc.bias[BOFF(L_MLP3) + c0 + i];
+                        s1[i] = (v > 0 ? s1[i] : 0.0f) + pw * hv;
+                        s2[i] = (v > 0 ? s2[i] : 0.0f) + pw * hv * hv;
+                    }
+                    t.st16(TC_SREG + c0, s1);
+                    t.st16(TC_SREG + 64 + c0, s2);
+                }
+                tc::tmem_st_wait();
+                wsum += pw;
+            }
+            // =========================================================== pooled latent, density head, compression
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int c0 = 32 * h + 16 * g;
+                float m[16], q[16];
+                t.ld16(TC_SREG + c0, m);
+                t.ld16(TC_SREG + 64 + c0, q);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) q[i] = q[i] - m[i] * m[i] * (2.0f - wsum);
+                if (A.dbg_latent && isamp < A.n_chunk) {
+                    float* o = A.dbg_latent + (size_t)(A.sample0 + isamp) * 128;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { o[c0 + i] = m[i]; o[64 + c0 + i] = q[i]; }
+                }
+                t.st_chunk(1, (c0 >> 3), make_uint4(tc::pack_bf16(m[0], m[1]), tc::pack_bf16(m[2], m[3]), tc::pack_bf16(m[4], m[5]), tc::pack_bf16(m[6], m[7])));
+                t.st_chunk(1, (c0 >> 3) + 1, make_uint4(tc::pack_bf16(m[8], m[9]), tc::pack_bf16(m[10], m[11]), tc::pack_bf16(m[12], m[13]), tc::pack_bf16(m[14], m[15])));
+                t.st_chunk(2, (c0 >> 3), make_uint4(tc::pack_bf16(q[0], q[1]), tc::pack_bf16(q[2], q[3]), tc::pack_bf16(q[4], q[5]), tc::pack_bf16(q[6], q[7])));
+                t.st_chunk(2, (c0 >> 3) + 1, make_uint4(tc::pack_bf16(q[8], q[9]), tc::pack_bf16(q[10], q[11]), tc::pack_bf16(q[12], q[13]), tc::pack_bf16(q[14], q[15])));
+            }
+            t.step(ST_Q1);
+            uint4 lat_a = make_uint4(0, 0, 0, 0), lat_b = make_uint4(0, 0, 0, 0);      // h=0: latent cols 0-15, h=1: cols 16-23
+            EPI(TA_SOFTPLUS, 32 * h, 2, BOFF(L_POST0) + 32 * h, 4, 4 * h);
+            if (h == 0) {
+                float x[16];
+                t.ld16(64, x);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] += c_tc.bias[BOFF(L_COMPRESS) + i];
+                lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
+                lat_b = make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15]));
+            } else {
+                float x[8];
+                t.ld8(80, x);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] += c_tc.bias[BOFF(L_COMPRESS) + 16 + i];
+                lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
+            }
+            t.step(ST_Q2);
+            EPI(TA_SOFTPLUS, 32 * h, 2, BOFF(L_POST1) + 32 * h, 0, 4 * h);
+            t.step(ST_Q3);
+            float o0, o1;
+            {
+                float x[8];
+                t.ld8(0, x);
+                o0 = x[0] + c_tc.bias[BOFF(L_POST2)];
+                o1 = x[1] + c_tc.bias[BOFF(L_POST2) + 1];
+            }
+            // =========================================================== texture branch per view
+#pragma unroll 1
+            for (int v = 0; v < V; ++v) {
+                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
+                if (tid == 0) {
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar, TC_SLOT);
+                    tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar);
+                }
+                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
+                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                // tail operand [lat24 | extras 8] in slot 2, ray difference (4) in slot 3 cols 0..15
+                if (h == 0) {
+                    t.st_chunk(2, 0, lat_a);
+                    t.st_chunk(2, 1, lat_b);
+                    t.st_chunk(3, 0, make_uint4(tc::pack_bf16(a0.w, a1.x), tc::pack_bf16(a1.y, a1.z), 0, 0));
+                    t.st_chunk(3, 1, make_uint4(0, 0, 0, 0));
+                } else {
+                    t.st_chunk(2, 2, lat_a);
+                    t.st_chunk(2, 3, *reinterpret_cast<const uint4*>(aux_row + v * TC_AUX_BYTES + 48));
+                }
+                tc_wait(&sh->rec_bar, t.rec_phase, sh->abort_flag, 401);
+                t.rec_phase ^= 1;
+                // ---- T1: attention layer 1 (ReLU) + ray encoder layer 1 (ELU)
+                t.step(ST_T1);
+                if (h == 0) {
+                    EPI(TA_RELU, 0, 3, -1, 4, 0);
+                    EPI(TA_ELU, 96, 1, BOFF(L_RAY0), 3, 2);
+                } else {
+                    EPI(TA_RELU, 48, 1, -1, 4, 6);
+                    EPI(TA_RELU, 64, 2, -1, 0, 0);
+                }
+                // ---- T2: attention layer 2 -> 6 sigmoid gates applied in place; ray encoder layer 2 -> dir40 to TMEM
+                t.step(ST_T2);
+                {
+                    float gt[8];
+                    t.ld8(0, gt);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) gt[i] = tc_act<TA_SIGMOID>(gt[i]);
+                    // slot 1 chunks: 0 -> g0, 1 -> g1, 2 -> g2, 3,4 -> g3, 5,6 -> g4, 7 -> [g3,g3,g4,g4,g0,g0,g0,g1]
+                    // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (c_tex_map1 / c_tex_map2)
+                    if (h == 0) {
+                        t.gate_chunk1(1, 0, gt[0]); t.gate_chunk1(1, 1, gt[1]); t.gate_chunk1(1, 2, gt[2]); t.gate_chunk1(1, 3, gt[3]);
+                        t.gate_chunk1(2, 0, gt[5]); t.gate_chunk1(2, 1, gt[5]);
+                    } else {
+                        t.gate_chunk1(1, 4, gt[3]); t.gate_chunk1(1, 5, gt[4]); t.gate_chunk1(1, 6, gt[4]);
+                        const float g7[8] = {gt[3], gt[3], gt[4], gt[4], gt[0], gt[0], gt[0], gt[1]};
+                        t.gate_chunk(1, 7, g7);
+                        t.gate_chunk1(2, 2, gt[5]);
+                        const float g3[8] = {gt[1], gt[1], gt[2], gt[2], gt[2], 1.0f, 1.0f, 1.0f};
+                        t.gate_chunk(2, 3, g3);
+                    }
+                    const int fcol = TC_SREG + 40 * v;
+                    if (h == 0) {
+                        float d[16], e[8];
+                        t.ld16(16, d);
+                        t.ld8(32, e);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + c_tc.bias[BOFF(L_RAY1) + i]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[i] = tc_act<TA_ELU>(e[i] + c_tc.bias[BOFF(L_RAY1) + 16 + i]);
+                        t.st16(fcol, d);
+                        t.st8(fcol + 16, e);
+                    } else {
+                        float d[16];
+                        t.ld16(40, d);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + c_tc.bias[BOFF(L_RAY1) + 24 + i]);
+                        t.st16(fcol + 24, d);
+                    }
+                    tc::tmem_st_wait();
+                }
+                // ---- T3: fused layer 1 (ReLU)
+                t.step(ST_T3);
+                if (h == 0) EPI(TA_RELU, 0, 3, -1, 4, 0);
+                else {
+                    EPI(TA_RELU, 48, 1, -1, 4, 6);
+                    EPI(TA_RELU, 64, 2, -1, 0, 0);
+                }
+                // ---- T4: fused layer 2 -> rgb_feat (40); source colour = channels 0..2; f = rgb_feat + dir
+                t.step(ST_T4);
+                {
+                    const int fcol = TC_SREG + 40 * v;
+                    if (h == 0) {
+                        float x[16], y[8], d[16], e[8];
+                        t.ld16(0, x);
+                        t.ld8(16, y);
+                        t.ld16(fcol, d);
+                        t.ld8(fcol + 16, e);
+                        const float src[8] = {x[0], x[1], x[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) d[i] += x[i];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[i] += y[i];
+                        t.st16(fcol, d);
+                        t.st8(fcol + 16, e);
+                        t.st8(TC_SRC + 4 * v, src);        // 4 columns per view; the 8-wide store only overlaps later views
+                    } else {
+                        float x[16], d[16];
+                        t.ld16(24, x);
+                        t.ld16(fcol + 24, d);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) d[i] += x[i];
+                        t.st16(fcol + 24, d);
+                    }
+                    tc::tmem_st_wait();
+                }
+            }
+            // =========================================================== IBRRenderingHead over the view axis
+            float wt[TC_MAXV], maskv = 0.f, sv[TC_MAXV];
+            {
+                float e[TC_MAXV], emin = 3.0e38f, sum = 0.f;
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    e[v] = 0.f; wt[v] = 0.f; sv[v] = -1e4f;
+                    if (v < V) {
+                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                        const float4 a2 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 32);
+                        maskv = a2.x;
+                        e[v] = __expf(c_tc.ani_al_abs * (a1.z - 1.0f));
+                        emin = fminf(emin, e[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) if (v < V) { e[v] = (e[v] - emin) * maskv; sum += e[v]; }
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) if (v < V) wt[v] = e[v] / (sum + 1e-8f);
+            }
+            {   // fused_mean_variance (src/utils.py:153-157): channels 0..23 (h=0) / 24..39 (h=1), 8 at a time;
+                // each thread reads back only the f columns it stored itself
+                const int g0 = h ? 3 : 0, g1 = h ? 5 : 3;
+#pragma unroll 1
+                for (int g = g0; g < g1; ++g) {
+                    float f[TC_MAXV][8], mean[8], var[8];
+#pragma unroll
+                    for (int v = 0; v < TC_MAXV; ++v) {
+                        if (v < V) t.ld8(TC_SREG + 40 * v + 8 * g, f[v]);
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[v][i] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float mu = 0.f;
+#pragma unroll
+                        for (int v = 0; v < TC_MAXV; ++v) mu += f[v][i] * wt[v];
+                        float va = 0.f;
+#pragma unroll
+                        for (int v = 0; v < TC_MAXV; ++v) { const float d = f[v][i] - mu; va += wt[v] * d * d; }
+                        mean[i] = mu; var[i] = va;
+                    }
+                    t.st_chunk(1, g, pack8(mean));                               // mean -> slot 1 cols 0..39
+                    if (g < 3) t.st_chunk(1, 5 + g, pack8(var));                 // var 0..23 -> slot 1 cols 40..63
+                    else t.st_chunk(2, g - 3, pack8(var));                       // var 24..39 -> slot 2 cols 0..15
+                }
+                if (h == 1) t.st_chunk(2, 7, make_uint4(0, 0, 0, 0));
+            }
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v) {
+                if (v >= V) break;
+                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
+                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                {   // f_v -> slot 2 cols 16..55
+                    const int g0 = h ? 3 : 0, g1 = h ? 5 : 3;
+#pragma unroll 1
+                    for (int g = g0; g < g1; ++g) {
+                        float f[8];
+                        t.ld8(TC_SREG + 40 * v + 8 * g, f);
+                        t.st_chunk(2, 2 + g, pack8(f));
+                    }
+                }
+                t.step(ST_I1);
+                EPI(TA_ELU, 32 * h, 2, BOFF(L_BASE0) + 32 * h, 4, 4 * h);
+                t.step(ST_I2);
+                float x[16];
+                t.ld16(16 * h, x);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + c_tc.bias[BOFF(L_BASE1) + 16 * h + i]);
+                {
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = x[i] * wt[v];
+                    t.st_chunk(0, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
+                    t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                }
+                t.step(ST_I3);
+                EPI(TA_ELU, 16 * h, 1, BOFF(L_VIS1_0) + 16 * h, 0, 4 + 2 * h);
+                t.step(ST_I4);
+                {
+                    float r[16], vv[8];
+                    t.ld16(16 * h, r);
+                    t.ld8(32, vv);
+                    const float vis = tc_act<TA_SIGMOID>(tc_act<TA_ELU>(vv[0] + c_tc.bias[BOFF(L_VIS1_1) + 32])) * maskv;
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        x[i] += tc_act<TA_ELU>(r[i] + c_tc.bias[BOFF(L_VIS1_1) + 16 * h + i]);
+                        y[i] = x[i] * vis;
+                    }
+                    t.st_chunk(0, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
+                    t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                }
+                t.step(ST_I5);
+                EPI(TA_ELU, 16 * h, 1, BOFF(L_VIS2_0) + 16 * h, 0, 4 + 2 * h);
+                t.step(ST_I6);
+                {
+                    float vv[8];
+                    t.ld8(0, vv);
+                    const float vis2 = tc_act<TA_SIGMOID>(vv[0] + c_tc.bias[BOFF(L_VIS2_1)]) * maskv;
+                    // out_layer input [x 32 | vis | ray_diff 4] -> slot 3 cols 0..47
+                    t.st_chunk(3, 2 * h, make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7])));
+                    t.st_chunk(3, 2 * h + 1, make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15])));
+                    if (h == 0) t.st_chunk(3, 4, make_uint4(tc::pack_bf16(vis2, a0.w), tc::pack_bf16(a1.x, a1.y), tc::pack_bf16(a1.z, 0.f), 0));
+                    else t.st_chunk(3, 5, make_uint4(0, 0, 0, 0));
+                }
+                t.step(ST_I7);
+                if (h == 0) EPI(TA_ELU, 0, 1, BOFF(L_OUT0), 3, 6);
+                t.step(ST_I8);
+                if (h == 0) EPI(TA_ELU, 0, 1, BOFF(L_OUT1), 0, 0);
+                t.step(ST_I9);
+                {
+                    float vv[8];
+                    t.ld8(0, vv);
+                    sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + c_tc.bias[BOFF(L_OUT2)]);
+                }
+            }
+            // =========================================================== softmax blend + eval_func (src/model.py:1634-1635, 1140-1160)
+            if (h == 0) {
+                float smax = -3.0e38f;
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) if (v < V) smax = fmaxf(smax, sv[v]);
+                float den = 0.f, rgb[3] = {0.f, 0.f, 0.f};
+                float src[16];
+                t.ld16(TC_SRC, src);
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    if (v < V) {
+                        const float e = __expf(sv[v] - smax);
+                        den += e;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) rgb[c] += src[4 * v + c] * e;
+                    }
+                }
+                const float inv = 1.0f / den;
+                if (isamp < A.n_chunk) {
+                    const size_t n = (size_t)(A.sample0 + isamp);
+                    if (A.raw_out) {
+                        float* o = A.raw_out + n * 5;
+                        o[0] = o0; o[1] = o1; o[2] = rgb[0] * inv; o[3] = rgb[1] * inv; o[4] = rgb[2] * inv;
+                    }
+                    if (A.rgba) {
+                        float* o = A.rgba + n * 5;
+                        o[0] = maskv * fmaxf(o1, 0.0f);
+                        o[1] = maskv * o0 + (1.0f - maskv) * 0.001f;
+                        o[2] = rgb[0] * inv; o[3] = rgb[1] * inv; o[4] = rgb[2] * inv;
+                    }
+                }
+            }
+            // all TMEM reads of this tile precede the next tile's MMAs (ordered by the next step barrier)
+        }
+    }
+    tc_teardown(sh, tid, warp, A.err);
+}
+
+// ================================================================================================ self test
+// D (128 x Npad, fp32) = bf16(A (128 x K)) * bf16(W (N x K))^T through the same slots / ring / issue / TMEM path as
+// k_mlp_tc, K <= 256 (multiple of 16), N <= 128.  c_tc holds a one-step table (index 0) built by tc_build_single.
+__global__ void __launch_bounds__(TC_THREADS, 2) k_tc_selftest(const unsigned char* wblob, const float* A_in, int K, int n_pad,
+                                                               float* D_out, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    tc_setup(smem, sh, tid, warp);
+    if (warp == 8) {
+        if (lane == 0) {
+            uint32_t cc = 0;
+            tc_load_step(0, cc, smem, wblob);
+        }
+    } else {
+        TcTile t;
+        tc_tile_init(t, smem, sh, warp, lane);
+        // operand: columns [64 s, 64 s + 64) of A -> slot s; this thread converts chunks 4 h .. 4 h + 3 of its row
+        for (int s = 0; s * 64 < K; ++s)
+            for (int c = 4 * t.half; c < 4 * t.half + 4; ++c) {
+                float f[8];
+                for (int i = 0; i < 8; ++i) {
+                    const int k = 64 * s + 8 * c + i;
+                    f[i] = k < K ? A_in[(size_t)t.row * K + k] : 0.0f;
+                }
+                t.st_chunk(s, c, pack8(f));
+            }
+        t.step(0);
+        for (int g = t.half; g * 16 < n_pad; g += 2) {       // 16-column groups alternate between the two row partners
+            const int c0 = 16 * g;
+            float v[16];
+            t.ld16(c0, v);
+            for (int i = 0; i < 16; ++i) D_out[(size_t)t.row * n_pad + c0 + i] = v[i];
+        }
+    }
+    tc_teardown(sh, tid, warp, err);
+}
+
+// One-step table for the self test: K columns over slots 0.., identity K order.
+static void tc_build_single(const float* W, int N, int K, TcTables& T, std::vector<uint16_t>& blob) {
+    memset(&T, 0, sizeof(T));
+    blob.clear();
+    const int n_pad = (N + 15) & ~15;
+    int n_ops = 0, n_chunks = 0;
+    uint32_t cur = 0;
+    for (int k0 = 0; k0 < K; k0 += 64) {
+        const int ncols = std::min(64, K - k0);
+        const uint32_t bytes = (uint32_t)n_pad * 128;
+        if (n_chunks == 0 || cur + bytes > TC_SLOT) {
+            if (n_ops) T.ops[n_ops - 1].last_in_chunk = 1;
+            T.chunks[n_chunks].src_off = (uint32_t)(blob.size() * 2);
+            T.chunks[n_chunks].bytes = 0;
+            ++n_chunks;
+            cur = 0;
+        }
+        TcOp& d = T.ops[n_ops++];
+        d.a_off = (uint32_t)((k0 / 64) * TC_SLOT);
+        d.b_off = cur;
+        d.idesc = tc::umma_idesc_bf16(128, n_pad);
+        d.d_col = 0;
+        d.nk = (uint8_t)(ncols / 16);
+        d.accum = k0 > 0;
+        d.chunk_rel = (uint8_t)(n_chunks - 1);
+        d.last_in_chunk = 0;
+        const size_t base = blob.size();
+        blob.resize(base + bytes / 2, 0);
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < ncols; ++k) {
+                const size_t byte = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ n) & 7) << 4) + (k & 7) * 2;
+                blob[base + byte / 2] = f2bf_host(W[(size_t)n * K + k0 + k]);
+            }
+        cur += bytes;
+        T.chunks[n_chunks - 1].bytes = cur;
+    }
+    T.ops[n_ops - 1].last_in_chunk = 1;
+    T.steps[0].op0 = 0; T.steps[0].nops = (uint16_t)n_ops; T.steps[0].chunk0 = 0; T.steps[0].nchunks = (uint16_t)n_chunks;
 }

@@ -13,6 +13,9 @@
 #include "gather.cuh"
 #include "mlp_simt.cuh"
 #include "composite.cuh"
+#ifndef VANERF_HOST_EMUL
+#include "mlp_tc.cuh"
+#endif
 
 struct DevBuf {
     void* p = nullptr;
@@ -37,7 +40,15 @@ struct vanerf_ctx {
     std::vector<TimedEv> evs;
 #endif
     // weights
-    DevBuf wblob, netdev, tcw;
+    DevBuf wblob, netdev;
+#ifndef VANERF_HOST_EMUL
+    // tensor-core path: step tables + bf16 weight images, bf16 maps / vertex tables, operand images, error flag
+    TcTables h_tc;                     // host copy of the __constant__ tables (weights + per-frame keypoints)
+    DevBuf tcw, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
+    FrameTc ft;
+    int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
+    int* tc_err_dev = nullptr;
+#endif
     NetDev h_net;
     bool have_weights = false;
     // frame
@@ -50,10 +61,8 @@ struct vanerf_ctx {
 };
 
 #ifndef VANERF_HOST_EMUL
-// tensor-core (tcgen05) path, defined in mlp_tc.cuh (included at the end of this file)
-static int tc_pack_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream);
-static int tc_shade_chunk(vanerf_ctx* ctx, const float* rec, long long sample0, int n_chunk, float* rgba, float* raw_out,
-                          cudaStream_t stream);
+// c_tc (__constant__) is one per device context: the vanerf_ctx whose tables it currently holds (re-uploaded on change)
+static const vanerf_ctx* g_tc_owner = nullptr;
 #endif
 
 static int ctx_fail(vanerf_ctx* ctx, cudaError_t e, const char* what, int line) {
@@ -104,13 +113,26 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     c->sm_count = sm;
     memset(&c->fr, 0, sizeof(c->fr));
     memset(&c->h_net, 0, sizeof(c->h_net));
+#ifndef VANERF_HOST_EMUL
+    if (cudaHostAlloc((void**)&c->tc_err_host, 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->tc_err_dev, c->tc_err_host, 0) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
+    memset(c->tc_err_host, 0, 8 * sizeof(int));
+    memset(&c->ft, 0, sizeof(c->ft));
+    memset(&c->h_tc, 0, sizeof(c->h_tc));
+#endif
     *out = c;
     return VANERF_OK;
 }
 
 void vanerf_ctx_destroy(vanerf_ctx* c) {
     if (!c) return;
-    DevBuf* all[] = {&c->wblob, &c->netdev, &c->tcw, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
+#ifndef VANERF_HOST_EMUL
+    if (g_tc_owner == c) g_tc_owner = nullptr;
+    DevBuf* tcb[] = {&c->tcw, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux};
+    for (DevBuf* b : tcb) if (b->p) cudaFree(b->p);
+    if (c->tc_err_host) cudaFreeHost(c->tc_err_host);
+#endif
+    DevBuf* all[] = {&c->wblob, &c->netdev, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
                      &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
                      &c->xyz_ndc, &c->xy11, &c->zbuf, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
                      &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab};
@@ -178,7 +200,17 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->netdev.p, &ctx->h_net, sizeof(NetDev), cudaMemcpyHostToDevice, (cudaStream_t)stream));
     CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // host staging buffers go out of scope
 #ifndef VANERF_HOST_EMUL
-    { int rc = tc_pack_weights(ctx, w, stream); if (rc) return rc; }
+    {   // tensor-core path: step tables + swizzled bf16 weight images
+        std::vector<uint16_t> img;
+        float kpt_keep[TC_MAXV * NKPT * 3];
+        memcpy(kpt_keep, ctx->h_tc.kpt, sizeof(kpt_keep));
+        tc_build(src, w->ani_al, ctx->h_tc, img);
+        memcpy(ctx->h_tc.kpt, kpt_keep, sizeof(kpt_keep));
+        if (g_tc_owner == ctx) g_tc_owner = nullptr;
+        ENSURE(ctx, ctx->tcw, img.size() * 2);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tcw.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    }
 #endif
     ctx->have_weights = true;
     return VANERF_OK;
@@ -261,6 +293,25 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     VANERF_LAUNCH(k_resolve_vis, cdiv(V * RASTER_S * RASTER_S, T), T, 0, stream, fr, (const unsigned long long*)ctx->zbuf.p, (float*)ctx->vis.p); CHECK_LAUNCH(ctx);
     VANERF_LAUNCH(k_vertex_tables, cdiv((long long)V * Nv * 104, T), T, 0, stream, fr, (const float*)ctx->xy11.p, f->vert_gfeat,
                   (float*)ctx->T64.p, (float*)ctx->T8.p, (float*)ctx->Ttex.p); CHECK_LAUNCH(ctx);
+#ifndef VANERF_HOST_EMUL
+    {   // bf16 companions for the tensor-core path; camera-space keypoints go to the constant tables
+        memset(ctx->h_tc.kpt, 0, sizeof(ctx->h_tc.kpt));
+        memcpy(ctx->h_tc.kpt, kc.data(), sizeof(float) * std::min<size_t>(kc.size(), (size_t)TC_MAXV * NKPT * 3));
+        if (g_tc_owner == ctx) g_tc_owner = nullptr;
+        const size_t t64n = (size_t)V * Nv * 64, t8n = (size_t)V * Nv * 8, ttn = (size_t)V * Nv * 32;
+        ENSURE(ctx, ctx->geo0b, g0n * 2); ENSURE(ctx, ctx->geo1b, g1n * 2); ENSURE(ctx, ctx->texb, txn * 2);
+        ENSURE(ctx, ctx->T64b, t64n * 2); ENSURE(ctx, ctx->T8b, t8n * 2); ENSURE(ctx, ctx->Ttexb, ttn * 2);
+        VANERF_LAUNCH(k_f32_to_bf16, cdiv(g0n, T), T, 0, stream, (const float*)ctx->geo0.p, (__nv_bfloat16*)ctx->geo0b.p, (long long)g0n); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_f32_to_bf16, cdiv(g1n, T), T, 0, stream, (const float*)ctx->geo1.p, (__nv_bfloat16*)ctx->geo1b.p, (long long)g1n); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_f32_to_bf16, cdiv(txn, T), T, 0, stream, (const float*)ctx->tex.p, (__nv_bfloat16*)ctx->texb.p, (long long)txn); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_f32_to_bf16, cdiv(t64n, T), T, 0, stream, (const float*)ctx->T64.p, (__nv_bfloat16*)ctx->T64b.p, (long long)t64n); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_f32_to_bf16, cdiv(t8n, T), T, 0, stream, (const float*)ctx->T8.p, (__nv_bfloat16*)ctx->T8b.p, (long long)t8n); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_ttex_bf16, cdiv(ttn, T), T, 0, stream, (const float*)ctx->Ttex.p, (__nv_bfloat16*)ctx->Ttexb.p, V * Nv); CHECK_LAUNCH(ctx);
+        ctx->ft.geo0 = (const __nv_bfloat16*)ctx->geo0b.p; ctx->ft.geo1 = (const __nv_bfloat16*)ctx->geo1b.p;
+        ctx->ft.tex = (const __nv_bfloat16*)ctx->texb.p; ctx->ft.T64 = (const __nv_bfloat16*)ctx->T64b.p;
+        ctx->ft.T8 = (const __nv_bfloat16*)ctx->T8b.p; ctx->ft.Ttex = (const __nv_bfloat16*)ctx->Ttexb.p;
+    }
+#endif
     if (vert_vis_out)
         CUDA_TRY(ctx, cudaMemcpyAsync(vert_vis_out, ctx->vis.p, (size_t)V * Nv * 4, cudaMemcpyDeviceToDevice, stream));
     ctx->have_frame = true;
@@ -302,6 +353,59 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
     return VANERF_OK;
 }
 
+#ifndef VANERF_HOST_EMUL
+// Tensor-core shading: gather (bf16 operand images) + fused MLP per chunk of 2 x SM-count tiles of 128 samples, so that
+// one chunk's images (<= 75 MB at V = 3) stay L2 resident between the two kernels.
+static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, const float* z, int S, long long N, const float* sdf,
+                    const int* nn, const unsigned char* qvis, float* rgba, unsigned char* valid, float* raw_out,
+                    float* dbg_latent, cudaStream_t stream, const float* pts_in, const float* view_in) {
+    const int V = ctx->fr.V;
+    if (V > TC_MAXV) {
+        snprintf(ctx->err, sizeof(ctx->err), "bf16 tensor-core path supports up to %d source views (got %d)", TC_MAXV, V);
+        return VANERF_ERR_UNSUPPORTED;
+    }
+    if (*ctx->tc_err_host) {
+        const int* e = ctx->tc_err_host;
+        snprintf(ctx->err, sizeof(ctx->err), "tensor-core kernel: a bounded wait gave up earlier (code %d; pending issue %d acc %d producer %d rec %d pe %d)",
+                 e[0], e[2], e[3], e[4], e[5], e[6]);
+        return VANERF_ERR_CUDA;
+    }
+    const int max_tiles = 2 * ctx->sm_count;
+    const long long chunk = (long long)max_tiles * TC_ROWS;
+    ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
+    ENSURE(ctx, ctx->tc_aux, (size_t)max_tiles * TC_ROWS * V * TC_AUX_BYTES);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    if (g_tc_owner != ctx) {            // stream-ordered: earlier launches on this stream have read the old tables
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_tc, &ctx->h_tc, sizeof(TcTables), 0, cudaMemcpyHostToDevice, stream));
+        g_tc_owner = ctx;
+    }
+    for (long long s0 = 0; s0 < N; s0 += chunk) {
+        const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
+        const int n_tiles = cdiv(nc, TC_ROWS);
+        {
+            TimedScope ts(ctx, KCL_GATHER, stream);
+            const int gblocks = min(cdiv((long long)n_tiles * TC_ROWS, GTC_THREADS / 8), ctx->sm_count * 8);
+            VANERF_LAUNCH(k_gather_tc, gblocks, GTC_THREADS, 0, stream, ctx->fr, ctx->ft, td, rays, z, pts_in, view_in, S, s0, nc, N,
+                          sdf, nn, qvis, (unsigned char*)ctx->tc_rec.p, (unsigned char*)ctx->tc_aux.p, valid);
+            CHECK_LAUNCH(ctx);
+        }
+        TimedScope ts(ctx, KCL_MLP, stream);
+        TcArgs a;
+        a.wblob = (const unsigned char*)ctx->tcw.p;
+        a.rec = (const unsigned char*)ctx->tc_rec.p; a.aux = (const unsigned char*)ctx->tc_aux.p;
+        a.V = V; a.n_chunk = nc; a.sample0 = s0;
+        a.rgba = rgba; a.raw_out = raw_out; a.dbg_latent = dbg_latent; a.err = ctx->tc_err_dev;
+        VANERF_LAUNCH(k_mlp_tc, min(n_tiles, max_tiles), TC_THREADS, TC_SMEM_BYTES, stream, a);
+        CHECK_LAUNCH(ctx);
+    }
+    return VANERF_OK;
+}
+#endif
+
 #define SHADE_CHUNK 65536      // samples per gather/MLP round; records: chunk * V * 1232 B
 
 // pts_in/view_in != NULL: explicit points and view directions ((N,3) each, R*S == N) instead of rays + depths
@@ -311,6 +415,10 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
                       const float* view_in = nullptr) {
     const long long N = (long long)R * S;
     const int V = ctx->fr.V;
+#ifndef VANERF_HOST_EMUL
+    if (precision == VANERF_BF16)
+        return tc_shade(ctx, td, rays, z, S, N, sdf, nn, qvis, rgba, valid, raw_out, dbg_latent, stream, pts_in, view_in);
+#endif
     const int chunk = (int)(N < SHADE_CHUNK ? N : SHADE_CHUNK);
     ENSURE(ctx, ctx->rec, (size_t)chunk * V * REC_STRIDE * 4);
     const size_t smem = mlp_simt_smem_floats(V) * sizeof(float);
@@ -330,13 +438,6 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
             CHECK_LAUNCH(ctx);
         }
         TimedScope ts(ctx, KCL_MLP, stream);
-#ifndef VANERF_HOST_EMUL
-        if (precision == VANERF_BF16) {
-            int rc = tc_shade_chunk(ctx, (const float*)ctx->rec.p, s0, nc, rgba, raw_out, stream);
-            if (rc) return rc;
-            continue;
-        }
-#endif
         const int mblocks = min(cdiv(nc, TS), ctx->sm_count);
         VANERF_LAUNCH(k_mlp_simt, mblocks, MLP_THREADS, smem, stream, (const NetDev*)ctx->netdev.p, ctx->fr.kpt_cam, V,
                       (const float*)ctx->rec.p, s0, nc, rgba, raw_out, dbg_latent);
@@ -363,6 +464,56 @@ int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* r
     if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
     return shade_impl(ctx, VANERF_FP32, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
                       (cudaStream_t)stream);
+}
+
+// test hooks of the tensor-core path ------------------------------------------------------------------------------
+// vanerf_shade_debug for the bf16 path (latent = pooled [mean | var] before bf16 rounding)
+int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
+                            const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
+                            float* raw_out, float* latent, void* stream) {
+    if (!ctx || !tar) return VANERF_ERR_INVALID;
+    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    return shade_impl(ctx, VANERF_BF16, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
+                      (cudaStream_t)stream);
+}
+// nonzero = a bounded wait inside a tensor-core kernel gave up (valid after the stream has been synchronised)
+int vanerf_tc_error(vanerf_ctx* ctx) {
+#ifndef VANERF_HOST_EMUL
+    return ctx ? *ctx->tc_err_host : 0;
+#else
+    (void)ctx;
+    return 0;
+#endif
+}
+// D (128, Npad) = bf16(A (128, K) dev) x bf16(W (N, K) host)^T through one tcgen05 step; K % 16 == 0, K <= 256, N <= 128
+int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host, int32_t K, int32_t N, float* D_dev, void* stream_) {
+#ifndef VANERF_HOST_EMUL
+    if (!ctx || !A_dev || !W_host || !D_dev || K <= 0 || K > 256 || (K & 15) || N <= 0 || N > 128) return ctx_invalid(ctx, "vanerf_tc_selftest");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    static TcTables T;
+    std::vector<uint16_t> img;
+    tc_build_single(W_host, N, K, T, img);
+    DevBuf blob;
+    ENSURE(ctx, blob, img.size() * 2);
+    g_tc_owner = nullptr;
+    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_tc, &T, sizeof(TcTables), 0, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(blob.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    VANERF_LAUNCH(k_tc_selftest, 1, TC_THREADS, TC_SMEM_BYTES, stream, (const unsigned char*)blob.p, A_dev, K,
+                  (N + 15) & ~15, D_dev, ctx->tc_err_dev);
+    CHECK_LAUNCH(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));
+    cudaFree(blob.p);
+    if (*ctx->tc_err_host) {
+        snprintf(ctx->err, sizeof(ctx->err), "tensor-core self test: bounded wait gave up (code %d)", *ctx->tc_err_host);
+        *ctx->tc_err_host = 0;
+        return VANERF_ERR_CUDA;
+    }
+    return VANERF_OK;
+#else
+    (void)A_dev; (void)W_host; (void)K; (void)N; (void)D_dev; (void)stream_;
+    return ctx_invalid(ctx, "tensor-core path needs the CUDA build");
+#endif
 }
 
 // VANeRF.query called directly on arbitrary points (src/model.py:748-877): geometry + gather + networks.
@@ -513,7 +664,3 @@ int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar,
 }
 
 }  // extern "C"
-
-#ifndef VANERF_HOST_EMUL
-#include "mlp_tc.cuh"
-#endif

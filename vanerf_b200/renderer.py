@@ -221,7 +221,8 @@ class Renderer:
         raw = self.empty((N, 5)) if want_raw else None
         if want_latent:
             lat = self.empty((N, 128))
-            st = self.lib.dll.vanerf_shade_debug(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
+            fn = self.lib.dll.vanerf_shade_debug if precision == L.FP32 else self.lib.dll.vanerf_shade_debug_bf16
+            st = fn(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
                                                  self._ptr(geo["nn"]), self._ptr(geo["qvis"]), self._ptr(rgba), self._ptr(valid),
                                                  self._ptr(raw), self._ptr(lat), self.stream)
             self.lib.check(self.ctx, st, "vanerf_shade_debug")
@@ -270,6 +271,22 @@ class Renderer:
                                               self._ptr(rgba), self.stream)
         self.lib.check(self.ctx, st, "vanerf_query_points")
         return raw, valid, rgba
+
+    def tc_error(self) -> int:
+        """Nonzero when a bounded wait inside a tensor-core kernel gave up (synchronises the device first)."""
+        if not self.lib.emulated:
+            torch.cuda.synchronize(self.device)
+        return int(self.lib.dll.vanerf_tc_error(self.ctx))
+
+    def tc_selftest(self, A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+        """bf16(A (128,K)) @ bf16(W (N,K))^T through one tcgen05 step (test hook)."""
+        K, N = A.shape[1], W.shape[0]
+        A = A.to(self.device, torch.float32).contiguous()
+        Wh = np.ascontiguousarray(W.detach().cpu().numpy(), np.float32)
+        D = self.empty((128, (N + 15) // 16 * 16))
+        st = self.lib.dll.vanerf_tc_selftest(self.ctx, self._ptr(A), Wh.ctypes.data, K, N, self._ptr(D), self.stream)
+        self.lib.check(self.ctx, st, "vanerf_tc_selftest")
+        return D[:, :N]
 
     KERNEL_CLASSES = ("setup", "rays", "geom", "gather", "mlp", "composite", "importance")
 
