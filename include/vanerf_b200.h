@@ -187,6 +187,9 @@ int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const flo
                             int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba,
                             uint8_t* valid, float* raw_out, float* latent, void* stream);
 int vanerf_tc_error(vanerf_ctx* ctx);
+/* Developer aid: cycle trace (tag, clock64) pairs of CTA 0 / thread 0 of the following tensor-core launches into
+ * buf dev (capacity, 2) int64; buf == NULL switches the trace off and returns the number of pairs recorded. */
+int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity);
 int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host, int32_t K, int32_t N, float* D_dev, void* stream);
 
 /* Number of kernels launched by this context since creation (for bench.py's gpu_launches). */

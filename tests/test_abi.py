@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _declared():
     h = open(os.path.join(ROOT, "include", "vanerf_b200.h")).read()
-    return sorted(set(re.findall(r"\b(vanerf_[a-z_]+)\s*\(", h)))
+    return sorted(set(re.findall(r"\b(vanerf_[a-z0-9_]+)\s*\(", h)))
 
 
 def test_cuda_library_exports_every_declared_symbol():

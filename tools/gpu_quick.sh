@@ -2,6 +2,7 @@
 # quick correctness + timing of the tensor-core path
 mkdir -p gpurun_out
 timeout 300 python tools/tc_debug.py > gpurun_out/tc_debug.log 2>&1; echo "tc_debug exit $?"; grep -E "selftest|shade|raw |FAILED" gpurun_out/tc_debug.log | head -30
+timeout 200 python tools/tc_trace.py 592 > gpurun_out/tc_trace.log 2>&1; echo "trace exit $?"; head -1 gpurun_out/tc_trace.log; tail -9 gpurun_out/tc_trace.log
 timeout 600 python bench.py --precision bf16 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench exit $?"
 python - <<'PY'
 import json

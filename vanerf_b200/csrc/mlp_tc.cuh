@@ -7,12 +7,14 @@
 //   IBRRenderingHead.forward               src/model.py:1600-1636
 //   eval_func                              src/model.py:1140-1160
 //
-// One CTA = one 128-sample tile at a time (persistent over tiles), two CTAs per SM so that one CTA's epilogue overlaps
-// the other's MMAs.  8 epilogue warps (two threads per row: warps w and w+4 share the TMEM lane quarter w and split the
-// columns) + 1 producer warp that streams weight images through a 2 x 16 KB ring with cp.async.bulk + mbarriers.
-// Activations never leave the SM: five 16 KB operand slots (128 rows x 64 bf16, K-major, 128B swizzle) are written by
-// the epilogue threads and read by tcgen05.mma through shared-memory descriptors; accumulators live in TMEM columns
-// [0,128), the view-pooling sums (later the per-view texture features) in columns [128,256).
+// One CTA per SM works on TWO 128-sample tiles at a time (persistent over tile pairs): each tile has its own group of
+// 8 warps (two threads per row: warps w and w+4 of the group share the TMEM lane quarter w and split the columns), its
+// own five 16 KB operand slots (128 rows x 64 bf16, K-major, 128B swizzle), its own accumulator / pooling TMEM columns
+// ([0,128) / [128,256) of its 256-column half) and its own barriers, and runs the layer sequence independently, so one
+// tile's epilogue overlaps the other's MMAs.  Both tiles consume the SAME weight stream: one producer warp brings the
+// weight images in once per tile pair through a 3 x 16 KB ring (cp.async.bulk + mbarriers; a ring slot is released when
+// the MMAs of both tiles that read it have completed).  Activations never leave the SM.  Step tables, biases and the
+// camera-space keypoints are copied to shared memory once per CTA.
 // The layer sequence is a table of "steps" (a set of MMAs whose results are consumed by one epilogue) built on the
 // host together with the weight images, so that the packer, the producer and the issuer cannot disagree.
 #pragma once
@@ -22,14 +24,22 @@
 #include "tc_prims.cuh"
 
 #define TC_NACT 5
-#define TC_NRING 2
-#define TC_EPI_THREADS 256
-#define TC_THREADS 288
-#define TC_TMEM_COLS 256
+#define TC_NRING 3
+#define TC_TILES 2                       // tiles in flight per CTA
+#define TC_EPI_THREADS 256               // threads of one tile group
+#define TC_THREADS (TC_TILES * TC_EPI_THREADS + 32)
+#define TC_TMEM_COLS 512
+#define TC_TMEM_TILE 256                 // TMEM columns per tile
 #define TC_SREG 128                      // TMEM columns of the pooling sums S1|S2, later the per-view f (40 each)
 #define TC_SRC 112                       // TMEM columns of the per-view source colours (4 per view)
 #define TC_MAXV 3
-#define TC_SMEM_BYTES ((TC_NACT + TC_NRING) * TC_SLOT + 256)
+#define TC_OFF_RING (TC_TILES * TC_NACT * TC_SLOT)
+#define TC_OFF_TAB (TC_OFF_RING + TC_NRING * TC_SLOT)
+#define TC_TAB_BYTES 8192                // >= sizeof(TcTables), multiple of 16
+#define TC_OFF_CTRL (TC_OFF_TAB + TC_TAB_BYTES)
+#define TC_OFF_TRACE (TC_OFF_CTRL + 512)
+#define TC_TRACE_N 1024                   // cycle-trace entries (tag << 48 | clock), developer aid
+#define TC_SMEM_BYTES (TC_OFF_TRACE + TC_TRACE_N * 8)
 
 enum TcStepId {
     ST_G1 = 0, ST_G2, ST_G3, ST_G4, ST_M0, ST_P0, ST_P1, ST_P2, ST_P3, ST_P4, ST_P5, ST_M1, ST_M2, ST_M3,
@@ -49,12 +59,12 @@ struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 64
 #define TC_MAX_CHUNKS 64
 #define TC_MAX_BIAS 1024
-struct TcTables {                        // lives in __constant__ memory (c_tc): uniform, low-latency reads
+struct TcTables {                        // global memory (context-owned); copied to shared memory once per CTA
+    alignas(16) float bias[TC_MAX_BIAS]; // read as float4 (offsets are multiples of 16 floats)
     TcStep steps[ST_COUNT];
     TcOp ops[TC_MAX_OPS];
     TcChunk chunks[TC_MAX_CHUNKS];
-    uint16_t bias_off[L_COUNT + 1];      // offset of each layer's bias in `bias` (layers without bias: zeros of their width)
-    float bias[TC_MAX_BIAS];
+    uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
     float kpt[TC_MAXV * NKPT * 3];       // keypoints in each source camera frame (per frame)
 };
@@ -219,16 +229,32 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
     T.ani_al_abs = fabsf(ani_al);
 }
 
+static_assert(sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
 // ================================================================================================ device
-__constant__ TcTables c_tc;
+// optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile): entries (tag << 48 | clock64 & (2^48-1)) collected in
+// shared memory (a few instructions per point) and flushed to d_tc_prof when the kernel ends
+__device__ long long* d_tc_prof = nullptr;
+__device__ int d_tc_prof_cap = 0;
+__device__ int d_tc_prof_n = 0;
+extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+__device__ __forceinline__ void tc_prof(int tag) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int* ctr = reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
+        const int i = *ctr;
+        if (i < 0 || i >= TC_TRACE_N) return;       // -1 = tracing off
+        reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[i] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+        *ctr = i + 1;
+    }
+}
 
-struct TcShared {                      // control block behind the operand slots
-    uint64_t wfull[TC_NRING], wempty[TC_NRING], acc_bar, rec_bar, pfree[3];
+struct TcShared {                      // control block behind the tables
+    uint64_t wfull[TC_NRING], wempty[TC_NRING], acc_bar[TC_TILES], rec_bar[TC_TILES], pfree[TC_TILES][3];
     uint32_t tmem_base;
     int abort_flag[8];                 // [0] first code that gave up, [1 + code/100] pending wait classes (tc_prims.cuh)
 };
 
 struct TcArgs {
+    const TcTables* tab;               // global copy of the tables
     const unsigned char* wblob;
     const unsigned char* rec;          // (n_tiles, V, 5, 16 KB)
     const unsigned char* aux;          // (n_tiles*128, V, 64)
@@ -253,48 +279,58 @@ __device__ __noinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile in
     return tc::mbar_wait(bar, parity, abort_flag, code);
 }
 
-// Publishes the calling threads' operand writes, then thread 0 issues the MMAs of step `st`.  All 256 tile threads
-// call it.  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (commit_to - 1), -1 = none.
-// cc = running weight-chunk counter (meaningful in thread 0 only); the new value is returned.
-__device__ __noinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem) {
+// Publishes the calling threads' operand writes, then the tile's first thread issues the MMAs of step `st`.  All 256
+// threads of tile group `tg` call it.  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (commit_to - 1),
+// -1 = none.  cc = running weight-chunk counter (meaningful in the issuing thread only); the new value is returned.
+__device__ __noinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
+    tc_prof(1000 + st);                  // epilogue of the previous step done (this thread)
     tc::fence_proxy_async();
     tc::tcgen05_fence_before();
-    tc::named_bar_sync(1, TC_EPI_THREADS);
-    if (threadIdx.x == 0) {
-        TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
-        const uint32_t act_u32 = tc::smem_u32(smem), ring_u32 = act_u32 + TC_NACT * TC_SLOT;
-        const uint32_t tmem = sh->tmem_base;
+    tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
+    tc_prof(2000 + st);                  // all operand writes published
+    if (threadIdx.x == tg * TC_EPI_THREADS) {
+        TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
+        const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
+        const uint32_t act_u32 = tc::smem_u32(smem) + tg * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(smem) + TC_OFF_RING;
+        const uint32_t tmem = sh->tmem_base + tg * TC_TMEM_TILE;
         tc::tcgen05_fence_after();
-        const TcStep S = c_tc.steps[st];
+        const TcStep S = tb->steps[st];
         int cur = -1;
         uint32_t slot_i = 0;
         for (int i = 0; i < S.nops; ++i) {
-            const TcOp op = c_tc.ops[S.op0 + i];
+            const TcOp op = tb->ops[S.op0 + i];
             if ((int)op.chunk_rel != cur) {
                 cur = op.chunk_rel;
                 const uint32_t c = cc + cur;
                 slot_i = c % TC_NRING;
+                tc_prof(7000);
                 tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
                 tc::tcgen05_fence_after();
+                tc_prof(7100);
             }
             const uint64_t ad = tc::umma_desc_sw128(act_u32 + op.a_off);
             const uint64_t bd = tc::umma_desc_sw128(ring_u32 + slot_i * TC_SLOT + op.b_off);
             for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
                 tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
+            tc_prof(7200);
             if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
+            tc_prof(7300);
         }
         cc += S.nchunks;
-        if (commit_to == 0) tc::umma_commit(&sh->acc_bar);
-        else if (commit_to > 0) tc::umma_commit(&sh->pfree[commit_to - 1]);
+        if (commit_to == 0) tc::umma_commit(&sh->acc_bar[tg]);
+        else if (commit_to > 0) tc::umma_commit(&sh->pfree[tg][commit_to - 1]);
+        tc_prof(3000 + st);              // MMAs issued (includes the wait for the weight chunk)
     }
     return cc;
 }
 
 struct TcTile {
-    unsigned char* act;       // operand slots (= dynamic smem base)
+    unsigned char* smem;      // dynamic smem base
+    unsigned char* act;       // operand slots of this tile
     TcShared* sh;
-    uint32_t trow;            // TMEM address of this thread's row, column 0
-    int row, half;
+    const TcTables* tb;       // tables in shared memory
+    uint32_t trow;            // TMEM address of this thread's row, first column of this tile's half
+    int row, half, tg;
     uint32_t acc_phase, rec_phase, pfree_phase[3], cc;
 
     __device__ __forceinline__ unsigned char* slot(int s) const { return act + s * TC_SLOT; }
@@ -330,11 +366,12 @@ struct TcTile {
         for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
         tc::tmem_st8(trow + col, r);
     }
-    __device__ __forceinline__ void issue(int st, int commit_to) { cc = tc_issue(st, commit_to, cc, act); }
+    __device__ __forceinline__ void issue(int st, int commit_to) { cc = tc_issue(st, commit_to, cc, smem, tg); }
     __device__ __forceinline__ void wait_acc(int st) {
-        tc_wait(&sh->acc_bar, acc_phase, sh->abort_flag, 200 + st);
+        tc_wait(&sh->acc_bar[tg], acc_phase, sh->abort_flag, 200 + st);
         acc_phase ^= 1;
         tc::tcgen05_fence_after();
+        tc_prof(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
     // multiply the 8 bf16 of a chunk by per-element gates
@@ -357,81 +394,112 @@ struct TcTile {
 // acc[col0 + 16 g .. +16) + bias -> ACT -> bf16 -> operand chunks (chunk0 + 2 g, +1) of the slot at `slot_base`, g < n16.
 // bias_idx < 0: no bias.  The TMEM load of group g + 1 is in flight while group g is processed.
 template <int ACT>
-__device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], int bias_idx, unsigned char* slot_base, int row, int chunk) {
+__device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const float* bias, unsigned char* slot_base, int row, int chunk) {
     float v[16];
+    if (bias) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = tc_act<ACT>(__uint_as_float(r[i]) + (bias_idx >= 0 ? c_tc.bias[bias_idx + i] : 0.0f));
+        for (int i = 0; i < 4; ++i) {
+            const float4 b4 = reinterpret_cast<const float4*>(bias)[i];      // shared memory, warp-uniform address
+            v[4 * i] = b4.x; v[4 * i + 1] = b4.y; v[4 * i + 2] = b4.z; v[4 * i + 3] = b4.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tc_act<ACT>(__uint_as_float(r[i]) + v[i]);
     *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk)) =
         make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk + 1)) =
         make_uint4(tc::pack_bf16(v[8], v[9]), tc::pack_bf16(v[10], v[11]), tc::pack_bf16(v[12], v[13]), tc::pack_bf16(v[14], v[15]));
 }
 template <int ACT>
-__device__ __noinline__ void tc_epi_store(uint32_t trow, int col0, int n16, int bias_idx, unsigned char* slot_base, int row, int chunk0) {
+__device__ __noinline__ void tc_epi_store(uint32_t trow, int col0, int n16, const float* bias, unsigned char* slot_base, int row, int chunk0) {
     uint32_t ra[16], rb[16];                 // double buffer: a buffer is only read after the wait that follows its load
+    tc_prof(7400);
     tc::tmem_ld16(trow + col0, ra);
 #pragma unroll 1
     for (int g = 0; g < n16; g += 2) {
         tc::tmem_ld_wait();
+        tc_prof(7500);
         if (g + 1 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 1), rb);
-        tc_epi_group<ACT>(ra, bias_idx >= 0 ? bias_idx + 16 * g : -1, slot_base, row, chunk0 + 2 * g);
+        tc_epi_group<ACT>(ra, bias ? bias + 16 * g : nullptr, slot_base, row, chunk0 + 2 * g);
         if (g + 1 < n16) {
             tc::tmem_ld_wait();
             if (g + 2 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 2), ra);
-            tc_epi_group<ACT>(rb, bias_idx >= 0 ? bias_idx + 16 * (g + 1) : -1, slot_base, row, chunk0 + 2 * (g + 1));
+            tc_epi_group<ACT>(rb, bias ? bias + 16 * (g + 1) : nullptr, slot_base, row, chunk0 + 2 * (g + 1));
         }
+        tc_prof(7600);
     }
 }
-#define EPI(ACT, col0, n16, bias_idx, s, chunk0) tc_epi_store<ACT>(t.trow, (col0), (n16), (bias_idx), t.slot(s), t.row, (chunk0))
-#define BOFF(l) ((int)c_tc.bias_off[l])
+#define EPI(ACT, col0, n16, bias, s, chunk0) tc_epi_store<ACT>(t.trow, (col0), (n16), (bias), t.slot(s), t.row, (chunk0))
+#define BIASP(l) (t.tb->bias + t.tb->bias_off[l])          // bias offsets are multiples of 16 floats
+#define NOBIAS ((const float*)nullptr)
 
-__device__ __forceinline__ int tex_gate_of(int ref) {       // gate group of a y96 input (src/networks.py:288-290)
-    return ref < 11 ? 0 : ref < 22 ? 1 : ref < 33 ? 2 : ref < 51 ? 3 : ref < 69 ? 4 : ref < 93 ? 5 : 6;
-}
-__constant__ int c_tex_map1[64] = {3, 4, 5, 6, 7, 8, 9, 10, 14, 15, 16, 17, 18, 19, 20, 21, 25, 26, 27, 28, 29, 30, 31, 32,
-                                   33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 51, 52, 53, 54, 55, 56, 57, 58,
-                                   59, 60, 61, 62, 63, 64, 65, 66, 49, 50, 67, 68, 0, 1, 2, 11};
-__constant__ int c_tex_map2[32] = {69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92,
-                                   12, 13, 22, 23, 24, 93, 94, 95};
 
-__device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, int tid, int warp) {
+// n_consumers = tile groups that issue MMAs (and therefore release ring slots)
+__device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, const TcTables* tab_g, int n_consumers) {
+    const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < TC_NRING; ++i) { tc::mbar_init(&sh->wfull[i], 1); tc::mbar_init(&sh->wempty[i], 1); }
-        tc::mbar_init(&sh->acc_bar, 1);
-        tc::mbar_init(&sh->rec_bar, 1);
-        for (int i = 0; i < 3; ++i) tc::mbar_init(&sh->pfree[i], 1);
+        for (int i = 0; i < TC_NRING; ++i) { tc::mbar_init(&sh->wfull[i], 1); tc::mbar_init(&sh->wempty[i], n_consumers); }
+        for (int g = 0; g < TC_TILES; ++g) {
+            tc::mbar_init(&sh->acc_bar[g], 1);
+            tc::mbar_init(&sh->rec_bar[g], 1);
+            for (int i = 0; i < 3; ++i) tc::mbar_init(&sh->pfree[g][i], 1);
+        }
         for (int i = 0; i < 8; ++i) sh->abort_flag[i] = 0;
         if ((tc::smem_u32(smem) & 1023u) != 0) sh->abort_flag[0] = 1;       // operand slots need 1024-byte alignment
+        *reinterpret_cast<int*>(smem + TC_OFF_CTRL + 504) = (blockIdx.x == 0 && d_tc_prof != nullptr) ? 0 : -1;
         tc::mbar_fence_init();
+    }
+    {   // tables -> shared memory
+        const uint4* src = reinterpret_cast<const uint4*>(tab_g);
+        uint4* dst = reinterpret_cast<uint4*>(smem + TC_OFF_TAB);
+        for (int i = tid; i < (int)(sizeof(TcTables) / 16); i += blockDim.x) dst[i] = src[i];
     }
     if (warp == 0) tc::tmem_alloc(&sh->tmem_base, TC_TMEM_COLS);
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
 }
-__device__ __forceinline__ void tc_teardown(TcShared* sh, int tid, int warp, int* err) {
+__device__ __forceinline__ void tc_teardown(TcShared* sh, int* err) {
+    const int tid = threadIdx.x, warp = tid >> 5;
     tc::tcgen05_fence_before();
     __syncthreads();
     tc::tcgen05_fence_after();
     if (tid == 0 && sh->abort_flag[0] && atomicCAS(err, 0, sh->abort_flag[0]) == 0)
         for (int i = 1; i < 8; ++i) err[i] = sh->abort_flag[i];
+    if (tid == 0 && blockIdx.x == 0 && d_tc_prof) {             // flush the cycle trace
+        const int n = *reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
+        int base = d_tc_prof_n;
+        for (int i = 0; i < n && base + i < d_tc_prof_cap; ++i) {
+            const unsigned long long e = reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[i];
+            d_tc_prof[2 * (base + i)] = (long long)(e >> 48);
+            d_tc_prof[2 * (base + i) + 1] = (long long)(e & 0xffffffffffffull);
+        }
+        d_tc_prof_n = min(base + max(n, 0), d_tc_prof_cap);
+    }
     if (warp == 0) tc::tmem_dealloc(sh->tmem_base, TC_TMEM_COLS);
 }
 __device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int warp, int lane) {
-    t.act = smem;
+    t.tg = warp >> 3;
+    t.smem = smem;
+    t.act = smem + t.tg * (TC_NACT * TC_SLOT);
     t.sh = sh;
+    t.tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
     t.row = 32 * (warp & 3) + lane;
-    t.half = warp >> 2;
-    t.trow = sh->tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    t.half = (warp >> 2) & 1;
+    t.trow = sh->tmem_base + t.tg * TC_TMEM_TILE + ((uint32_t)(32 * (warp & 3)) << 16);
     t.acc_phase = 0; t.rec_phase = 0; t.cc = 0;
     t.pfree_phase[0] = t.pfree_phase[1] = t.pfree_phase[2] = 0;
 }
 __device__ __noinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
-    unsigned char* ring = smem + TC_NACT * TC_SLOT;
-    const TcStep S = c_tc.steps[st];
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
+    const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
+    unsigned char* ring = smem + TC_OFF_RING;
+    const TcStep S = tb->steps[st];
     for (int c = 0; c < S.nchunks; ++c, ++cc) {
-        const TcChunk ch = c_tc.chunks[S.chunk0 + c];
+        const TcChunk ch = tb->chunks[S.chunk0 + c];
         const uint32_t s = cc % TC_NRING;
         tc::mbar_wait(&sh->wempty[s], ((cc / TC_NRING) & 1) ^ 1, sh->abort_flag, 300 + st);
         tc::mbar_arrive_expect_tx(&sh->wfull[s], ch.bytes);
@@ -439,20 +507,21 @@ __device__ __noinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* s
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
+    unsigned char* smem = tc_smem_raw;
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = A.V;
     const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
-    tc_setup(smem, sh, tid, warp);
+    const int n_pairs = (n_tiles + TC_TILES - 1) / TC_TILES;
+    tc_setup(smem, sh, A.tab, TC_TILES);
 
-    if (warp == 8) {
+    if (warp == TC_TILES * 8) {
         // ===================================================== weight producer
         if (lane == 0) {
             uint32_t cc = 0;
 #pragma unroll 1
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
 #pragma unroll 1
                 for (int v = 0; v < V; ++v)
 #pragma unroll 1
@@ -473,30 +542,37 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
         // ===================================================== tile threads
         TcTile t;
         tc_tile_init(t, smem, sh, warp, lane);
-        const int row = t.row, h = t.half;
+        const int row = t.row, h = t.half, tg = t.tg;
+        const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's MMAs and record loads
 
 #pragma unroll 1
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int isamp = tile * TC_ROWS + row;
-            const unsigned char* aux_row = A.aux + (size_t)isamp * V * TC_AUX_BYTES;
+        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+            // an odd tile count leaves the last pair's second group without a tile: it re-runs the last tile (the ring
+            // needs both consumers) and stores nothing
+            const int tile_raw = pair * TC_TILES + tg;
+            const int tile = min(tile_raw, n_tiles - 1);
+            const int isamp = tile_raw < n_tiles ? tile * TC_ROWS + row : A.n_chunk;
+            const unsigned char* aux_row = A.aux + ((size_t)tile * TC_ROWS + row) * V * TC_AUX_BYTES;
             float wsum = 0.0f;
             // =========================================================== per-view geometry branch
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
                 const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
-                if (tid == 0) {        // all MMAs that read slots 0..3 have completed (last wait_acc)
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar, 4 * TC_SLOT);
-                    for (int s = 0; s < 4; ++s) tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar);
+                if (leader) {          // all MMAs that read slots 0..3 have completed (last wait_acc)
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], 4 * TC_SLOT);
+                    for (int s = 0; s < 4; ++s) tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
                 }
                 const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
                 const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
                 const float pw = a1.w;
-                tc_wait(&sh->rec_bar, t.rec_phase, sh->abort_flag, 400);
+                tc_prof(5000 + v);
+                tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 400);
                 t.rec_phase ^= 1;
+                tc_prof(5100 + v);
                 // ---- G1: attention layer 1 of both scales
                 t.step(ST_G1);
-                if (h == 0) EPI(TA_RELU, 0, 1, -1, 3, 6);
-                else EPI(TA_RELU, 16, 1, -1, 4, 0);
+                if (h == 0) EPI(TA_RELU, 0, 1, NOBIAS, 3, 6);
+                else EPI(TA_RELU, 16, 1, NOBIAS, 4, 0);
                 // ---- G2: attention layer 2 -> sigmoid gates, applied in place
                 t.step(ST_G2);
                 {
@@ -514,12 +590,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                 }
                 // ---- G3: fused layer 1 (ReLU)
                 t.step(ST_G3);
-                EPI(TA_RELU, 32 * h, 2, -1, 4, 4 * h);
-                if (h == 0) EPI(TA_RELU, 64, 1, -1, 3, 6);
+                EPI(TA_RELU, 32 * h, 2, NOBIAS, 4, 4 * h);
+                if (h == 0) EPI(TA_RELU, 64, 1, NOBIAS, 3, 6);
                 // ---- G4: fused layer 2 -> out64 (slot 0), out8 (slot 3 cols 48..63)
                 t.step(ST_G4);
-                EPI(TA_NONE, 32 * h, 2, -1, 0, 4 * h);
-                if (h == 1) EPI(TA_NONE, 64, 1, -1, 3, 6);
+                EPI(TA_NONE, 32 * h, 2, NOBIAS, 0, 4 * h);
+                if (h == 1) EPI(TA_NONE, 64, 1, NOBIAS, 3, 6);
                 // ---- MLP layer 0: out64 part, then the positional encoding in 6 operand slots through a 3-slot ring
                 t.issue(ST_M0, -1);
 #pragma unroll 1
@@ -527,14 +603,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     const int ps = s % 3;
                     const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : 4;
                     if (s >= 3) {
-                        tc_wait(&sh->pfree[ps], t.pfree_phase[ps], sh->abort_flag, 500 + s);
+                        tc_wait(&sh->pfree[tg][ps], t.pfree_phase[ps], sh->abort_flag, 500 + s);
                         t.pfree_phase[ps] ^= 1;
                     }
                     const int nk = s < 5 ? 4 : 1;
 #pragma unroll 1
                     for (int j = 0; j < nk; ++j) {
                         const int kp = 8 * s + 2 * j + h;
-                        const float* kc = c_tc.kpt + (v * NKPT + kp) * 3;
+                        const float* kc = t.tb->kpt + (v * NKPT + kp) * 3;
                         const float dx = a0.x - kc[0], dy = a0.y - kc[1], dz = a0.z - kc[2];
                         const float w = __expf(-(dx * dx + dy * dy + dz * dz) * 50.0f);       // exp(-d^2 / (2 * 0.1^2))
                         float s1, c1;
@@ -551,14 +627,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                 // drain the ring-slot barriers committed by P3, P4 (slots 0, 1): already complete (MMAs complete in order)
 #pragma unroll 1
                 for (int ps = 0; ps < 2; ++ps) {
-                    tc_wait(&sh->pfree[ps], t.pfree_phase[ps], sh->abort_flag, 510 + ps);
+                    tc_wait(&sh->pfree[tg][ps], t.pfree_phase[ps], sh->abort_flag, 510 + ps);
                     t.pfree_phase[ps] ^= 1;
                 }
-                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP0) + 64 * h, 1 + h, 0);        // h0 -> slots 1, 2
+                EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP0) + 64 * h, 1 + h, 0);        // h0 -> slots 1, 2
                 t.step(ST_M1);
-                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP1) + 64 * h, h ? 0 : 4, 0);   // h1 -> slots 4, 0
+                EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP1) + 64 * h, h ? 0 : 4, 0);   // h1 -> slots 4, 0
                 t.step(ST_M2);
-                EPI(TA_SOFTPLUS, 64 * h, 4, BOFF(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
+                EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
                 t.step(ST_M3);
                 // ---- weighted pooling sums over views in TMEM: S1 += w h3, S2 += w h3^2 (pool_ops, src/utils.py:854-880)
 #pragma unroll 1
@@ -569,7 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     if (v > 0) { t.ld16(TC_SREG + c0, s1); t.ld16(TC_SREG + 64 + c0, s2); }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float hv = x[i] + c_tc.bias[BOFF(L_MLP3) + c0 + i];
+                        const float hv = x[i] + BIASP(L_MLP3)[c0 + i];
                         s1[i] = (v > 0 ? s1[i] : 0.0f) + pw * hv;
                         s2[i] = (v > 0 ? s2[i] : 0.0f) + pw * hv * hv;
                     }
@@ -600,38 +676,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
             }
             t.step(ST_Q1);
             uint4 lat_a = make_uint4(0, 0, 0, 0), lat_b = make_uint4(0, 0, 0, 0);      // h=0: latent cols 0-15, h=1: cols 16-23
-            EPI(TA_SOFTPLUS, 32 * h, 2, BOFF(L_POST0) + 32 * h, 4, 4 * h);
+            EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST0) + 32 * h, 4, 4 * h);
             if (h == 0) {
                 float x[16];
                 t.ld16(64, x);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] += c_tc.bias[BOFF(L_COMPRESS) + i];
+                for (int i = 0; i < 16; ++i) x[i] += BIASP(L_COMPRESS)[i];
                 lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
                 lat_b = make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15]));
             } else {
                 float x[8];
                 t.ld8(80, x);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] += c_tc.bias[BOFF(L_COMPRESS) + 16 + i];
+                for (int i = 0; i < 8; ++i) x[i] += BIASP(L_COMPRESS)[16 + i];
                 lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
             }
             t.step(ST_Q2);
-            EPI(TA_SOFTPLUS, 32 * h, 2, BOFF(L_POST1) + 32 * h, 0, 4 * h);
+            EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST1) + 32 * h, 0, 4 * h);
             t.step(ST_Q3);
             float o0, o1;
             {
                 float x[8];
                 t.ld8(0, x);
-                o0 = x[0] + c_tc.bias[BOFF(L_POST2)];
-                o1 = x[1] + c_tc.bias[BOFF(L_POST2) + 1];
+                o0 = x[0] + BIASP(L_POST2)[0];
+                o1 = x[1] + BIASP(L_POST2)[1];
             }
             // =========================================================== texture branch per view
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
                 const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
-                if (tid == 0) {
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar, TC_SLOT);
-                    tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar);
+                if (leader) {
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], TC_SLOT);
+                    tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
                 }
                 const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
                 const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
@@ -645,16 +721,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     t.st_chunk(2, 2, lat_a);
                     t.st_chunk(2, 3, *reinterpret_cast<const uint4*>(aux_row + v * TC_AUX_BYTES + 48));
                 }
-                tc_wait(&sh->rec_bar, t.rec_phase, sh->abort_flag, 401);
+                tc_prof(5200 + v);
+                tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 401);
                 t.rec_phase ^= 1;
+                tc_prof(5300 + v);
                 // ---- T1: attention layer 1 (ReLU) + ray encoder layer 1 (ELU)
                 t.step(ST_T1);
                 if (h == 0) {
-                    EPI(TA_RELU, 0, 3, -1, 4, 0);
-                    EPI(TA_ELU, 96, 1, BOFF(L_RAY0), 3, 2);
+                    EPI(TA_RELU, 0, 3, NOBIAS, 4, 0);
+                    EPI(TA_ELU, 96, 1, BIASP(L_RAY0), 3, 2);
                 } else {
-                    EPI(TA_RELU, 48, 1, -1, 4, 6);
-                    EPI(TA_RELU, 64, 2, -1, 0, 0);
+                    EPI(TA_RELU, 48, 1, NOBIAS, 4, 6);
+                    EPI(TA_RELU, 64, 2, NOBIAS, 0, 0);
                 }
                 // ---- T2: attention layer 2 -> 6 sigmoid gates applied in place; ray encoder layer 2 -> dir40 to TMEM
                 t.step(ST_T2);
@@ -664,7 +742,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
 #pragma unroll
                     for (int i = 0; i < 6; ++i) gt[i] = tc_act<TA_SIGMOID>(gt[i]);
                     // slot 1 chunks: 0 -> g0, 1 -> g1, 2 -> g2, 3,4 -> g3, 5,6 -> g4, 7 -> [g3,g3,g4,g4,g0,g0,g0,g1]
-                    // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (c_tex_map1 / c_tex_map2)
+                    // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (kTexMap1 / kTexMap2)
                     if (h == 0) {
                         t.gate_chunk1(1, 0, gt[0]); t.gate_chunk1(1, 1, gt[1]); t.gate_chunk1(1, 2, gt[2]); t.gate_chunk1(1, 3, gt[3]);
                         t.gate_chunk1(2, 0, gt[5]); t.gate_chunk1(2, 1, gt[5]);
@@ -682,26 +760,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                         t.ld16(16, d);
                         t.ld8(32, e);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + c_tc.bias[BOFF(L_RAY1) + i]);
+                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + BIASP(L_RAY1)[i]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) e[i] = tc_act<TA_ELU>(e[i] + c_tc.bias[BOFF(L_RAY1) + 16 + i]);
+                        for (int i = 0; i < 8; ++i) e[i] = tc_act<TA_ELU>(e[i] + BIASP(L_RAY1)[16 + i]);
                         t.st16(fcol, d);
                         t.st8(fcol + 16, e);
                     } else {
                         float d[16];
                         t.ld16(40, d);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + c_tc.bias[BOFF(L_RAY1) + 24 + i]);
+                        for (int i = 0; i < 16; ++i) d[i] = tc_act<TA_ELU>(d[i] + BIASP(L_RAY1)[24 + i]);
                         t.st16(fcol + 24, d);
                     }
                     tc::tmem_st_wait();
                 }
                 // ---- T3: fused layer 1 (ReLU)
                 t.step(ST_T3);
-                if (h == 0) EPI(TA_RELU, 0, 3, -1, 4, 0);
+                if (h == 0) EPI(TA_RELU, 0, 3, NOBIAS, 4, 0);
                 else {
-                    EPI(TA_RELU, 48, 1, -1, 4, 6);
-                    EPI(TA_RELU, 64, 2, -1, 0, 0);
+                    EPI(TA_RELU, 48, 1, NOBIAS, 4, 6);
+                    EPI(TA_RELU, 64, 2, NOBIAS, 0, 0);
                 }
                 // ---- T4: fused layer 2 -> rgb_feat (40); source colour = channels 0..2; f = rgb_feat + dir
                 t.step(ST_T4);
@@ -743,7 +821,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                         const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
                         const float4 a2 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 32);
                         maskv = a2.x;
-                        e[v] = __expf(c_tc.ani_al_abs * (a1.z - 1.0f));
+                        e[v] = __expf(t.tb->ani_al_abs * (a1.z - 1.0f));
                         emin = fminf(emin, e[v]);
                     }
                 }
@@ -797,12 +875,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     }
                 }
                 t.step(ST_I1);
-                EPI(TA_ELU, 32 * h, 2, BOFF(L_BASE0) + 32 * h, 4, 4 * h);
+                EPI(TA_ELU, 32 * h, 2, BIASP(L_BASE0) + 32 * h, 4, 4 * h);
                 t.step(ST_I2);
                 float x[16];
                 t.ld16(16 * h, x);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + c_tc.bias[BOFF(L_BASE1) + 16 * h + i]);
+                for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_BASE1)[16 * h + i]);
                 {
                     float y[16];
 #pragma unroll
@@ -811,29 +889,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
                 }
                 t.step(ST_I3);
-                EPI(TA_ELU, 16 * h, 1, BOFF(L_VIS1_0) + 16 * h, 0, 4 + 2 * h);
+                EPI(TA_ELU, 16 * h, 1, BIASP(L_VIS1_0) + 16 * h, 0, 4 + 2 * h);
                 t.step(ST_I4);
                 {
                     float r[16], vv[8];
                     t.ld16(16 * h, r);
                     t.ld8(32, vv);
-                    const float vis = tc_act<TA_SIGMOID>(tc_act<TA_ELU>(vv[0] + c_tc.bias[BOFF(L_VIS1_1) + 32])) * maskv;
+                    const float vis = tc_act<TA_SIGMOID>(tc_act<TA_ELU>(vv[0] + BIASP(L_VIS1_1)[32])) * maskv;
                     float y[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        x[i] += tc_act<TA_ELU>(r[i] + c_tc.bias[BOFF(L_VIS1_1) + 16 * h + i]);
+                        x[i] += tc_act<TA_ELU>(r[i] + BIASP(L_VIS1_1)[16 * h + i]);
                         y[i] = x[i] * vis;
                     }
                     t.st_chunk(0, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
                     t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
                 }
                 t.step(ST_I5);
-                EPI(TA_ELU, 16 * h, 1, BOFF(L_VIS2_0) + 16 * h, 0, 4 + 2 * h);
+                EPI(TA_ELU, 16 * h, 1, BIASP(L_VIS2_0) + 16 * h, 0, 4 + 2 * h);
                 t.step(ST_I6);
                 {
                     float vv[8];
                     t.ld8(0, vv);
-                    const float vis2 = tc_act<TA_SIGMOID>(vv[0] + c_tc.bias[BOFF(L_VIS2_1)]) * maskv;
+                    const float vis2 = tc_act<TA_SIGMOID>(vv[0] + BIASP(L_VIS2_1)[0]) * maskv;
                     // out_layer input [x 32 | vis | ray_diff 4] -> slot 3 cols 0..47
                     t.st_chunk(3, 2 * h, make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7])));
                     t.st_chunk(3, 2 * h + 1, make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15])));
@@ -841,14 +919,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     else t.st_chunk(3, 5, make_uint4(0, 0, 0, 0));
                 }
                 t.step(ST_I7);
-                if (h == 0) EPI(TA_ELU, 0, 1, BOFF(L_OUT0), 3, 6);
+                if (h == 0) EPI(TA_ELU, 0, 1, BIASP(L_OUT0), 3, 6);
                 t.step(ST_I8);
-                if (h == 0) EPI(TA_ELU, 0, 1, BOFF(L_OUT1), 0, 0);
+                if (h == 0) EPI(TA_ELU, 0, 1, BIASP(L_OUT1), 0, 0);
                 t.step(ST_I9);
                 {
                     float vv[8];
                     t.ld8(0, vv);
-                    sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + c_tc.bias[BOFF(L_OUT2)]);
+                    sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + BIASP(L_OUT2)[0]);
                 }
             }
             // =========================================================== softmax blend + eval_func (src/model.py:1634-1635, 1140-1160)
@@ -883,27 +961,28 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_mlp_tc(TcArgs A) {
                     }
                 }
             }
+            tc_prof(6000);
             // all TMEM reads of this tile precede the next tile's MMAs (ordered by the next step barrier)
         }
     }
-    tc_teardown(sh, tid, warp, A.err);
+    tc_teardown(sh, A.err);
 }
 
 // ================================================================================================ self test
 // D (128 x Npad, fp32) = bf16(A (128 x K)) * bf16(W (N x K))^T through the same slots / ring / issue / TMEM path as
 // k_mlp_tc, K <= 256 (multiple of 16), N <= 128.  c_tc holds a one-step table (index 0) built by tc_build_single.
-__global__ void __launch_bounds__(TC_THREADS, 2) k_tc_selftest(const unsigned char* wblob, const float* A_in, int K, int n_pad,
-                                                               float* D_out, int* err) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + (TC_NACT + TC_NRING) * TC_SLOT);
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_selftest(const TcTables* tab, const unsigned char* wblob, const float* A_in, int K,
+                                                               int n_pad, float* D_out, int* err) {
+    unsigned char* smem = tc_smem_raw;
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    tc_setup(smem, sh, tid, warp);
-    if (warp == 8) {
+    tc_setup(smem, sh, tab, 1);                  // only tile group 0 consumes the ring
+    if (warp == TC_TILES * 8) {
         if (lane == 0) {
             uint32_t cc = 0;
             tc_load_step(0, cc, smem, wblob);
         }
-    } else {
+    } else if (warp < 8) {
         TcTile t;
         tc_tile_init(t, smem, sh, warp, lane);
         // operand: columns [64 s, 64 s + 64) of A -> slot s; this thread converts chunks 4 h .. 4 h + 3 of its row
@@ -924,7 +1003,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_tc_selftest(const unsigned ch
             for (int i = 0; i < 16; ++i) D_out[(size_t)t.row * n_pad + c0 + i] = v[i];
         }
     }
-    tc_teardown(sh, tid, warp, err);
+    tc_teardown(sh, err);
 }
 
 // One-step table for the self test: K columns over slots 0.., identity K order.

@@ -43,8 +43,9 @@ struct vanerf_ctx {
     DevBuf wblob, netdev;
 #ifndef VANERF_HOST_EMUL
     // tensor-core path: step tables + bf16 weight images, bf16 maps / vertex tables, operand images, error flag
-    TcTables h_tc;                     // host copy of the __constant__ tables (weights + per-frame keypoints)
-    DevBuf tcw, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
+    TcTables h_tc;                     // host copy of the step tables / biases (weights) + camera-space keypoints (frame)
+    bool tc_tab_dirty = true;
+    DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
     int* tc_err_dev = nullptr;
@@ -59,11 +60,6 @@ struct vanerf_ctx {
     // scratch
     DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
 };
-
-#ifndef VANERF_HOST_EMUL
-// c_tc (__constant__) is one per device context: the vanerf_ctx whose tables it currently holds (re-uploaded on change)
-static const vanerf_ctx* g_tc_owner = nullptr;
-#endif
 
 static int ctx_fail(vanerf_ctx* ctx, cudaError_t e, const char* what, int line) {
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "CUDA error %d (%s) at %s [vanerf_b200.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
@@ -127,8 +123,7 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
 void vanerf_ctx_destroy(vanerf_ctx* c) {
     if (!c) return;
 #ifndef VANERF_HOST_EMUL
-    if (g_tc_owner == c) g_tc_owner = nullptr;
-    DevBuf* tcb[] = {&c->tcw, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux};
+    DevBuf* tcb[] = {&c->tcw, &c->tctab, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux};
     for (DevBuf* b : tcb) if (b->p) cudaFree(b->p);
     if (c->tc_err_host) cudaFreeHost(c->tc_err_host);
 #endif
@@ -206,7 +201,7 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
         memcpy(kpt_keep, ctx->h_tc.kpt, sizeof(kpt_keep));
         tc_build(src, w->ani_al, ctx->h_tc, img);
         memcpy(ctx->h_tc.kpt, kpt_keep, sizeof(kpt_keep));
-        if (g_tc_owner == ctx) g_tc_owner = nullptr;
+        ctx->tc_tab_dirty = true;
         ENSURE(ctx, ctx->tcw, img.size() * 2);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tcw.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
@@ -297,7 +292,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     {   // bf16 companions for the tensor-core path; camera-space keypoints go to the constant tables
         memset(ctx->h_tc.kpt, 0, sizeof(ctx->h_tc.kpt));
         memcpy(ctx->h_tc.kpt, kc.data(), sizeof(float) * std::min<size_t>(kc.size(), (size_t)TC_MAXV * NKPT * 3));
-        if (g_tc_owner == ctx) g_tc_owner = nullptr;
+        ctx->tc_tab_dirty = true;
         const size_t t64n = (size_t)V * Nv * 64, t8n = (size_t)V * Nv * 8, ttn = (size_t)V * Nv * 32;
         ENSURE(ctx, ctx->geo0b, g0n * 2); ENSURE(ctx, ctx->geo1b, g1n * 2); ENSURE(ctx, ctx->texb, txn * 2);
         ENSURE(ctx, ctx->T64b, t64n * 2); ENSURE(ctx, ctx->T8b, t8n * 2); ENSURE(ctx, ctx->Ttexb, ttn * 2);
@@ -370,7 +365,7 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
                  e[0], e[2], e[3], e[4], e[5], e[6]);
         return VANERF_ERR_CUDA;
     }
-    const int max_tiles = 2 * ctx->sm_count;
+    const int max_tiles = TC_TILES * ctx->sm_count;
     const long long chunk = (long long)max_tiles * TC_ROWS;
     ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
     ENSURE(ctx, ctx->tc_aux, (size_t)max_tiles * TC_ROWS * V * TC_AUX_BYTES);
@@ -379,9 +374,11 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
-    if (g_tc_owner != ctx) {            // stream-ordered: earlier launches on this stream have read the old tables
-        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_tc, &ctx->h_tc, sizeof(TcTables), 0, cudaMemcpyHostToDevice, stream));
-        g_tc_owner = ctx;
+    if (ctx->tc_tab_dirty) {            // stream-ordered: earlier launches on this stream have read the old tables
+        ENSURE(ctx, ctx->tctab, sizeof(TcTables));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tctab.p, &ctx->h_tc, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(stream));          // h_tc may change again before an async copy would read it
+        ctx->tc_tab_dirty = false;
     }
     for (long long s0 = 0; s0 < N; s0 += chunk) {
         const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
@@ -395,11 +392,11 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         }
         TimedScope ts(ctx, KCL_MLP, stream);
         TcArgs a;
-        a.wblob = (const unsigned char*)ctx->tcw.p;
+        a.tab = (const TcTables*)ctx->tctab.p; a.wblob = (const unsigned char*)ctx->tcw.p;
         a.rec = (const unsigned char*)ctx->tc_rec.p; a.aux = (const unsigned char*)ctx->tc_aux.p;
         a.V = V; a.n_chunk = nc; a.sample0 = s0;
         a.rgba = rgba; a.raw_out = raw_out; a.dbg_latent = dbg_latent; a.err = ctx->tc_err_dev;
-        VANERF_LAUNCH(k_mlp_tc, min(n_tiles, max_tiles), TC_THREADS, TC_SMEM_BYTES, stream, a);
+        VANERF_LAUNCH(k_mlp_tc, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a);
         CHECK_LAUNCH(ctx);
     }
     return VANERF_OK;
@@ -476,6 +473,24 @@ int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const flo
     return shade_impl(ctx, VANERF_BF16, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
                       (cudaStream_t)stream);
 }
+// Cycle trace of CTA 0 / thread 0 of the next k_mlp_tc launches: buf dev (capacity, 2) int64 pairs (tag, clock64), NULL = off.
+// Returns the number of pairs recorded so far (after a stream synchronise) when buf == NULL.
+int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity) {
+#ifndef VANERF_HOST_EMUL
+    if (!ctx) return VANERF_ERR_INVALID;
+    int n = 0, zero = 0;
+    if (!buf) {
+        if (cudaMemcpyFromSymbol(&n, d_tc_prof_n, sizeof(int)) != cudaSuccess) return VANERF_ERR_CUDA;
+        capacity = 0;
+    }
+    if (cudaMemcpyToSymbol(d_tc_prof, &buf, sizeof(buf)) != cudaSuccess || cudaMemcpyToSymbol(d_tc_prof_cap, &capacity, sizeof(int)) != cudaSuccess ||
+        cudaMemcpyToSymbol(d_tc_prof_n, &zero, sizeof(int)) != cudaSuccess) return VANERF_ERR_CUDA;
+    return n;
+#else
+    (void)ctx; (void)buf; (void)capacity;
+    return 0;
+#endif
+}
 // nonzero = a bounded wait inside a tensor-core kernel gave up (valid after the stream has been synchronised)
 int vanerf_tc_error(vanerf_ctx* ctx) {
 #ifndef VANERF_HOST_EMUL
@@ -493,17 +508,17 @@ int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host,
     static TcTables T;
     std::vector<uint16_t> img;
     tc_build_single(W_host, N, K, T, img);
-    DevBuf blob;
+    DevBuf blob, tab;
     ENSURE(ctx, blob, img.size() * 2);
-    g_tc_owner = nullptr;
-    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_tc, &T, sizeof(TcTables), 0, cudaMemcpyHostToDevice, stream));
+    ENSURE(ctx, tab, sizeof(TcTables));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tab.p, &T, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(blob.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    VANERF_LAUNCH(k_tc_selftest, 1, TC_THREADS, TC_SMEM_BYTES, stream, (const unsigned char*)blob.p, A_dev, K,
+    VANERF_LAUNCH(k_tc_selftest, 1, TC_THREADS, TC_SMEM_BYTES, stream, (const TcTables*)tab.p, (const unsigned char*)blob.p, A_dev, K,
                   (N + 15) & ~15, D_dev, ctx->tc_err_dev);
     CHECK_LAUNCH(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-    cudaFree(blob.p);
+    cudaFree(blob.p); cudaFree(tab.p);
     if (*ctx->tc_err_host) {
         snprintf(ctx->err, sizeof(ctx->err), "tensor-core self test: bounded wait gave up (code %d)", *ctx->tc_err_host);
         *ctx->tc_err_host = 0;
