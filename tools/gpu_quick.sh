@@ -1,9 +1,9 @@
 #!/bin/bash
-# quick correctness + timing of the tensor-core path
+# quick correctness + timing of the tensor-core path; a failing / hanging correctness pass skips the bench
 mkdir -p gpurun_out
-timeout 300 python tools/tc_debug.py > gpurun_out/tc_debug.log 2>&1; echo "tc_debug exit $?"; grep -E "selftest|shade|raw |FAILED" gpurun_out/tc_debug.log | head -30
-timeout 200 python tools/tc_trace.py 592 > gpurun_out/tc_trace.log 2>&1; echo "trace exit $?"; head -1 gpurun_out/tc_trace.log; tail -9 gpurun_out/tc_trace.log
-timeout 600 python bench.py --precision bf16 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench exit $?"
+timeout 150 python tools/tc_debug.py > gpurun_out/tc_debug.log 2>&1; rc=$?; echo "tc_debug exit $rc"; grep -E "selftest|shade|raw |latent|rgba|FAILED" gpurun_out/tc_debug.log | head -40
+if [ $rc -ne 0 ] || grep -q "tc_error=[1-9]" gpurun_out/tc_debug.log; then echo "correctness pass failed: no bench"; exit 1; fi
+timeout 300 python bench.py --precision bf16 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err; echo "bench exit $?"
 python - <<'PY'
 import json
 try:

@@ -27,7 +27,9 @@
 #define TC_NRING 3
 #define TC_TILES 2                       // tiles in flight per CTA
 #define TC_EPI_THREADS 256               // threads of one tile group
-#define TC_THREADS (TC_TILES * TC_EPI_THREADS + 32)
+#define TC_THREADS (TC_TILES * TC_EPI_THREADS + 128)   // + one warpgroup: weight producer warp and three parked warps
+#define TC_REGS_EPI 112                  // registers of a tile thread after setmaxnreg (kernel is compiled for 96)
+#define TC_REGS_PROD 24                  // registers of the producer warpgroup (gives 72 x 128 back to the pool)
 #define TC_TMEM_COLS 512
 #define TC_TMEM_TILE 256                 // TMEM columns per tile
 #define TC_SREG 128                      // TMEM columns of the pooling sums S1|S2, later the per-view f (40 each)
@@ -35,10 +37,14 @@
 #define TC_MAXV 3
 #define TC_OFF_RING (TC_TILES * TC_NACT * TC_SLOT)
 #define TC_OFF_TAB (TC_OFF_RING + TC_NRING * TC_SLOT)
-#define TC_TAB_BYTES 8192                // >= sizeof(TcTables), multiple of 16
+#define TC_TAB_BYTES 9216                // >= sizeof(TcTables), multiple of 16
 #define TC_OFF_CTRL (TC_OFF_TAB + TC_TAB_BYTES)
 #define TC_OFF_TRACE (TC_OFF_CTRL + 512)
+#ifdef VANERF_TC_TRACE
 #define TC_TRACE_N 1024                   // cycle-trace entries (tag << 48 | clock), developer aid
+#else
+#define TC_TRACE_N 0
+#endif
 #define TC_SMEM_BYTES (TC_OFF_TRACE + TC_TRACE_N * 8)
 
 enum TcStepId {
@@ -64,9 +70,10 @@ struct TcTables {                        // global memory (context-owned); copie
     TcStep steps[ST_COUNT];
     TcOp ops[TC_MAX_OPS];
     TcChunk chunks[TC_MAX_CHUNKS];
+    alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
+    alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
-    float kpt[TC_MAXV * NKPT * 3];       // keypoints in each source camera frame (per frame)
 };
 
 // ================================================================================================ host: script + images
@@ -227,16 +234,22 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
     }
     T.bias_off[L_COUNT] = (uint16_t)boff;
     T.ani_al_abs = fabsf(ani_al);
+    for (int sc = 0; sc < 2; ++sc) {
+        const vanerf_linear& L = *src[sc ? L_GEO8_AT1 : L_GEO_AT1];
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 10; ++i) T.at2[sc * 36 + j * 12 + i] = L.w[(size_t)j * L.in_dim + i];
+    }
 }
 
 static_assert(sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
 // ================================================================================================ device
-// optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile): entries (tag << 48 | clock64 & (2^48-1)) collected in
-// shared memory (a few instructions per point) and flushed to d_tc_prof when the kernel ends
+// Optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile), compiled in only with -DVANERF_TC_TRACE: entries
+// (tag << 48 | clock64 & (2^48-1)) collected in shared memory and flushed to d_tc_prof when the kernel ends.
+extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+#ifdef VANERF_TC_TRACE
 __device__ long long* d_tc_prof = nullptr;
 __device__ int d_tc_prof_cap = 0;
 __device__ int d_tc_prof_n = 0;
-extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
 __device__ __forceinline__ void tc_prof(int tag) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         int* ctr = reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
@@ -246,11 +259,16 @@ __device__ __forceinline__ void tc_prof(int tag) {
         *ctr = i + 1;
     }
 }
+#define TC_PROF(tag) tc_prof(tag)
+#else
+#define TC_PROF(tag) ((void)0)
+#endif
 
 struct TcShared {                      // control block behind the tables
     uint64_t wfull[TC_NRING], wempty[TC_NRING], acc_bar[TC_TILES], rec_bar[TC_TILES], pfree[TC_TILES][3];
     uint32_t tmem_base;
     int abort_flag[8];                 // [0] first code that gave up, [1 + code/100] pending wait classes (tc_prims.cuh)
+    int stop[TC_TILES];                // per tile group: leave the persistent loop (abort seen by the group's leader)
 };
 
 struct TcArgs {
@@ -267,59 +285,107 @@ struct TcArgs {
 };
 
 enum TcAct { TA_NONE = 0, TA_RELU, TA_SOFTPLUS, TA_SIGMOID, TA_ELU };
+__device__ __forceinline__ float tc_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <int ACT> __device__ __forceinline__ float tc_act(float x) {
     if (ACT == TA_RELU) return fmaxf(x, 0.0f);
     if (ACT == TA_SOFTPLUS) return fmaxf(x, 0.0f) + 0.01f * __logf(1.0f + __expf(-100.0f * fabsf(x)));   // Softplus(beta=100)
-    if (ACT == TA_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-x));
-    if (ACT == TA_ELU) return x > 0.0f ? x : __expf(x) - 1.0f;
+    if (ACT == TA_SIGMOID) return __fdividef(1.0f, 1.0f + tc_ex2(-1.44269504f * x));
+    if (ACT == TA_ELU) return x > 0.0f ? x : tc_ex2(1.44269504f * x) - 1.0f;
     return x;
 }
+// Softplus(beta = 100, threshold 20) of two values, evaluated on packed bf16 (the result is rounded to bf16 anyway):
+//   softplus(x) = max(x, 0) + log1p(exp(-100 |x|)) / 100,   w = exp(-100 |x|) in (0, 1] by one packed MUFU ex2,
+//   log1p(w) / 100 ~ w (c0 + w (c1 + w c2))  (least squares on [0, 1], |error| < 7e-6 in the output).
+// Above the reference's threshold (100 x > 20) the correction is < 2.1e-11, i.e. the reference's linear branch.
+__device__ __forceinline__ uint32_t tc_softplus2(float a, float b) {
+    uint32_t h, na, w, p, r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+    asm("{.reg .b32 n;\n\t"
+        "neg.bf16x2 n, %1;\n\t"
+        "min.bf16x2 %0, %1, n;}" : "=r"(na) : "r"(h));                    // -|h|
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(w) : "r"(na), "r"(0x43104310u));      // * 144 (100 log2 e)
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(w) : "r"(w));
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(w), "r"(0x3A933A93u), "r"(0xBB85BB85u));   // c2 = 1.1234e-3, c1 = -4.0516e-3
+    asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(w), "r"(0x3C223C22u));              // c0 = 9.8642e-3
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(p) : "r"(p), "r"(w));
+    asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(h), "r"(0x3F803F80u), "r"(0u));        // max(h, 0)
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(p));
+    return r;
+}
+template <int ACT> __device__ __forceinline__ uint32_t tc_pack_act(float a, float b) {    // act(a) -> low half, act(b) -> high half
+    if (ACT == TA_SOFTPLUS) return tc_softplus2(a, b);
+    if (ACT == TA_RELU) {
+        uint32_t d;
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+        return d;
+    }
+    return tc::pack_bf16(tc_act<ACT>(a), tc_act<ACT>(b));
+}
+__device__ __forceinline__ uint32_t tc_mul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t tc_dup_bf16(float g) { return tc::pack_bf16(g, g); }
 
-__device__ __noinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
+__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
     return tc::mbar_wait(bar, parity, abort_flag, code);
 }
 
-// Publishes the calling threads' operand writes, then the tile's first thread issues the MMAs of step `st`.  All 256
-// threads of tile group `tg` call it.  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (commit_to - 1),
-// -1 = none.  cc = running weight-chunk counter (meaningful in the issuing thread only); the new value is returned.
-__device__ __noinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
-    tc_prof(1000 + st);                  // epilogue of the previous step done (this thread)
+// Issues the MMAs of step `st` (one thread).  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier
+// (commit_to - 1), -1 = none.  cc = running weight-chunk counter; the new value is returned.
+__device__ __forceinline__ uint32_t tc_issue_ops(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
+    const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
+    const uint32_t act_u32 = tc::smem_u32(smem) + tg * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(smem) + TC_OFF_RING;
+    const uint32_t tmem = sh->tmem_base + tg * TC_TMEM_TILE;
+    const TcStep S = tb->steps[st];
+    int cur = -1;
+    uint32_t slot_i = 0;
+#pragma unroll 1
+    for (int i = 0; i < S.nops; ++i) {
+        const TcOp op = tb->ops[S.op0 + i];
+        if ((int)op.chunk_rel != cur) {
+            cur = op.chunk_rel;
+            const uint32_t c = cc + cur;
+            slot_i = c % TC_NRING;
+            TC_PROF(7000);
+            tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
+            tc::tcgen05_fence_after();
+            TC_PROF(7100);
+        }
+        const uint64_t ad = tc::umma_desc_sw128(act_u32 + op.a_off);
+        const uint64_t bd = tc::umma_desc_sw128(ring_u32 + slot_i * TC_SLOT + op.b_off);
+#pragma unroll 1
+        for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
+            tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
+        TC_PROF(7200);
+        if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
+        TC_PROF(7300);
+    }
+    cc += S.nchunks;
+    if (commit_to == 0) tc::umma_commit(&sh->acc_bar[tg]);
+    else if (commit_to > 0) tc::umma_commit(&sh->pfree[tg][commit_to - 1]);
+    TC_PROF(3000 + st);              // MMAs issued (includes the wait for the weight chunk)
+    return cc;
+}
+// Publishes the calling threads' operand writes (and orders their TMEM reads before the coming MMAs), then the
+// tile's first thread issues the MMAs of step `st`.  All 256 threads of tile group `tg` call it and synchronise on the
+// tile's named barrier (a non-blocking arrive would let a fast warp lap the issuing warp in the PE steps, which have
+// no accumulator wait in between).
+__device__ __forceinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
+    TC_PROF(1000 + st);                  // epilogue of the previous step done (this thread)
     tc::fence_proxy_async();
     tc::tcgen05_fence_before();
     tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
-    tc_prof(2000 + st);                  // all operand writes published
-    if (threadIdx.x == tg * TC_EPI_THREADS) {
-        TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
-        const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
-        const uint32_t act_u32 = tc::smem_u32(smem) + tg * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(smem) + TC_OFF_RING;
-        const uint32_t tmem = sh->tmem_base + tg * TC_TMEM_TILE;
+    TC_PROF(2000 + st);                  // all operand writes published
+    if ((threadIdx.x & (TC_EPI_THREADS - 1)) == 0) {
         tc::tcgen05_fence_after();
-        const TcStep S = tb->steps[st];
-        int cur = -1;
-        uint32_t slot_i = 0;
-        for (int i = 0; i < S.nops; ++i) {
-            const TcOp op = tb->ops[S.op0 + i];
-            if ((int)op.chunk_rel != cur) {
-                cur = op.chunk_rel;
-                const uint32_t c = cc + cur;
-                slot_i = c % TC_NRING;
-                tc_prof(7000);
-                tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
-                tc::tcgen05_fence_after();
-                tc_prof(7100);
-            }
-            const uint64_t ad = tc::umma_desc_sw128(act_u32 + op.a_off);
-            const uint64_t bd = tc::umma_desc_sw128(ring_u32 + slot_i * TC_SLOT + op.b_off);
-            for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
-                tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
-            tc_prof(7200);
-            if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
-            tc_prof(7300);
-        }
-        cc += S.nchunks;
-        if (commit_to == 0) tc::umma_commit(&sh->acc_bar[tg]);
-        else if (commit_to > 0) tc::umma_commit(&sh->pfree[tg][commit_to - 1]);
-        tc_prof(3000 + st);              // MMAs issued (includes the wait for the weight chunk)
+        cc = tc_issue_ops(st, commit_to, cc, smem, tg);
     }
     return cc;
 }
@@ -330,15 +396,17 @@ struct TcTile {
     TcShared* sh;
     const TcTables* tb;       // tables in shared memory
     uint32_t trow;            // TMEM address of this thread's row, first column of this tile's half
+    uint32_t row_off, rx;     // byte offset of this thread's row inside a slot, row & 7 (swizzle key)
     int row, half, tg;
-    uint32_t acc_phase, rec_phase, pfree_phase[3], cc;
+    uint32_t acc_phase, rec_phase, pfree_bits, cc;       // pfree_bits: bit ps = phase parity of PE ring slot ps
 
     __device__ __forceinline__ unsigned char* slot(int s) const { return act + s * TC_SLOT; }
+    __device__ __forceinline__ uint32_t coff(int chunk) const { return row_off + (((uint32_t)chunk ^ rx) << 4); }
     __device__ __forceinline__ void st_chunk(int s, int chunk, const uint4& q) const {
-        *reinterpret_cast<uint4*>(slot(s) + tc::slot_chunk_off(row, chunk)) = q;
+        *reinterpret_cast<uint4*>(slot(s) + coff(chunk)) = q;
     }
     __device__ __forceinline__ uint4 ld_chunk(int s, int chunk) const {
-        return *reinterpret_cast<const uint4*>(slot(s) + tc::slot_chunk_off(row, chunk));
+        return *reinterpret_cast<const uint4*>(slot(s) + coff(chunk));
     }
     __device__ __forceinline__ void ld16(int col, float (&v)[16]) const {
         uint32_t r[16];
@@ -371,68 +439,61 @@ struct TcTile {
         tc_wait(&sh->acc_bar[tg], acc_phase, sh->abort_flag, 200 + st);
         acc_phase ^= 1;
         tc::tcgen05_fence_after();
-        tc_prof(4000 + st);              // accumulator complete
+        TC_PROF(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
-    // multiply the 8 bf16 of a chunk by per-element gates
-    __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
-        float f[8];
-        unpack8(ld_chunk(s, chunk), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] *= g[i];
-        st_chunk(s, chunk, pack8(f));
+    // multiply the 8 bf16 of a chunk by one gate (packed bf16 multiply; g2 = the gate in both halves)
+    __device__ __forceinline__ void gate_chunk1(int s, int chunk, uint32_t g2) const {
+        uint4 q = ld_chunk(s, chunk);
+        q.x = tc_mul2(q.x, g2); q.y = tc_mul2(q.y, g2); q.z = tc_mul2(q.z, g2); q.w = tc_mul2(q.w, g2);
+        st_chunk(s, chunk, q);
     }
-    __device__ __forceinline__ void gate_chunk1(int s, int chunk, float g) const {
-        float f[8];
-        unpack8(ld_chunk(s, chunk), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] *= g;
-        st_chunk(s, chunk, pack8(f));
+    __device__ __forceinline__ void gate_chunk4(int s, int chunk, uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3) const {
+        uint4 q = ld_chunk(s, chunk);
+        q.x = tc_mul2(q.x, g0); q.y = tc_mul2(q.y, g1); q.z = tc_mul2(q.z, g2); q.w = tc_mul2(q.w, g3);
+        st_chunk(s, chunk, q);
     }
 };
 
-// acc[col0 + 16 g .. +16) + bias -> ACT -> bf16 -> operand chunks (chunk0 + 2 g, +1) of the slot at `slot_base`, g < n16.
-// bias_idx < 0: no bias.  The TMEM load of group g + 1 is in flight while group g is processed.
+// acc[16 columns in r] + bias -> ACT -> bf16 -> operand chunks `chunk`, `chunk + 1` of the slot at `slot_base`.
 template <int ACT>
-__device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const float* bias, unsigned char* slot_base, int row, int chunk) {
+__device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const float* bias, unsigned char* slot_base, const TcTile& t, int chunk) {
     float v[16];
     if (bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 b4 = reinterpret_cast<const float4*>(bias)[i];      // shared memory, warp-uniform address
-            v[4 * i] = b4.x; v[4 * i + 1] = b4.y; v[4 * i + 2] = b4.z; v[4 * i + 3] = b4.w;
+            v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = tc_act<ACT>(__uint_as_float(r[i]) + v[i]);
-    *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk)) =
-        make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
-    *reinterpret_cast<uint4*>(slot_base + tc::slot_chunk_off(row, chunk + 1)) =
-        make_uint4(tc::pack_bf16(v[8], v[9]), tc::pack_bf16(v[10], v[11]), tc::pack_bf16(v[12], v[13]), tc::pack_bf16(v[14], v[15]));
+    *reinterpret_cast<uint4*>(slot_base + t.coff(chunk)) =
+        make_uint4(tc_pack_act<ACT>(v[0], v[1]), tc_pack_act<ACT>(v[2], v[3]), tc_pack_act<ACT>(v[4], v[5]), tc_pack_act<ACT>(v[6], v[7]));
+    *reinterpret_cast<uint4*>(slot_base + t.coff(chunk + 1)) =
+        make_uint4(tc_pack_act<ACT>(v[8], v[9]), tc_pack_act<ACT>(v[10], v[11]), tc_pack_act<ACT>(v[12], v[13]), tc_pack_act<ACT>(v[14], v[15]));
 }
-template <int ACT>
-__device__ __noinline__ void tc_epi_store(uint32_t trow, int col0, int n16, const float* bias, unsigned char* slot_base, int row, int chunk0) {
+// acc[col0 + 16 g .. +16) -> chunks (chunk0 + 2 g, +1), g < N16.  The TMEM load of group g + 1 is in flight while
+// group g is processed.
+template <int ACT, int N16>
+__device__ __forceinline__ void tc_epi_store(const TcTile& t, int col0, const float* bias, unsigned char* slot_base, int chunk0) {
     uint32_t ra[16], rb[16];                 // double buffer: a buffer is only read after the wait that follows its load
-    tc_prof(7400);
-    tc::tmem_ld16(trow + col0, ra);
-#pragma unroll 1
-    for (int g = 0; g < n16; g += 2) {
+    tc::tmem_ld16(t.trow + col0, ra);
+#pragma unroll
+    for (int g = 0; g < N16; g += 2) {
         tc::tmem_ld_wait();
-        tc_prof(7500);
-        if (g + 1 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 1), rb);
-        tc_epi_group<ACT>(ra, bias ? bias + 16 * g : nullptr, slot_base, row, chunk0 + 2 * g);
-        if (g + 1 < n16) {
+        if (g + 1 < N16) tc::tmem_ld16(t.trow + col0 + 16 * (g + 1), rb);
+        tc_epi_group<ACT>(ra, bias ? bias + 16 * g : nullptr, slot_base, t, chunk0 + 2 * g);
+        if (g + 1 < N16) {
             tc::tmem_ld_wait();
-            if (g + 2 < n16) tc::tmem_ld16(trow + col0 + 16 * (g + 2), ra);
-            tc_epi_group<ACT>(rb, bias ? bias + 16 * (g + 1) : nullptr, slot_base, row, chunk0 + 2 * (g + 1));
+            if (g + 2 < N16) tc::tmem_ld16(t.trow + col0 + 16 * (g + 2), ra);
+            tc_epi_group<ACT>(rb, bias ? bias + 16 * (g + 1) : nullptr, slot_base, t, chunk0 + 2 * (g + 1));
         }
-        tc_prof(7600);
     }
 }
-#define EPI(ACT, col0, n16, bias, s, chunk0) tc_epi_store<ACT>(t.trow, (col0), (n16), (bias), t.slot(s), t.row, (chunk0))
+#define EPI(ACT, col0, n16, bias, s, chunk0) tc_epi_store<ACT, n16>(t, (col0), (bias), t.slot(s), (chunk0))
 #define BIASP(l) (t.tb->bias + t.tb->bias_off[l])          // bias offsets are multiples of 16 floats
 #define NOBIAS ((const float*)nullptr)
 
@@ -448,8 +509,11 @@ __device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, cons
             for (int i = 0; i < 3; ++i) tc::mbar_init(&sh->pfree[g][i], 1);
         }
         for (int i = 0; i < 8; ++i) sh->abort_flag[i] = 0;
+        for (int g = 0; g < TC_TILES; ++g) sh->stop[g] = 0;
         if ((tc::smem_u32(smem) & 1023u) != 0) sh->abort_flag[0] = 1;       // operand slots need 1024-byte alignment
+#ifdef VANERF_TC_TRACE
         *reinterpret_cast<int*>(smem + TC_OFF_CTRL + 504) = (blockIdx.x == 0 && d_tc_prof != nullptr) ? 0 : -1;
+#endif
         tc::mbar_fence_init();
     }
     {   // tables -> shared memory
@@ -469,6 +533,7 @@ __device__ __forceinline__ void tc_teardown(TcShared* sh, int* err) {
     tc::tcgen05_fence_after();
     if (tid == 0 && sh->abort_flag[0] && atomicCAS(err, 0, sh->abort_flag[0]) == 0)
         for (int i = 1; i < 8; ++i) err[i] = sh->abort_flag[i];
+#ifdef VANERF_TC_TRACE
     if (tid == 0 && blockIdx.x == 0 && d_tc_prof) {             // flush the cycle trace
         const int n = *reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
         int base = d_tc_prof_n;
@@ -479,6 +544,7 @@ __device__ __forceinline__ void tc_teardown(TcShared* sh, int* err) {
         }
         d_tc_prof_n = min(base + max(n, 0), d_tc_prof_cap);
     }
+#endif
     if (warp == 0) tc::tmem_dealloc(sh->tmem_base, TC_TMEM_COLS);
 }
 __device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int warp, int lane) {
@@ -488,16 +554,19 @@ __device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcS
     t.sh = sh;
     t.tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
     t.row = 32 * (warp & 3) + lane;
+    t.row_off = (uint32_t)((t.row >> 3) * 1024 + (t.row & 7) * 128);
+    t.rx = (uint32_t)(t.row & 7);
     t.half = (warp >> 2) & 1;
     t.trow = sh->tmem_base + t.tg * TC_TMEM_TILE + ((uint32_t)(32 * (warp & 3)) << 16);
     t.acc_phase = 0; t.rec_phase = 0; t.cc = 0;
-    t.pfree_phase[0] = t.pfree_phase[1] = t.pfree_phase[2] = 0;
+    t.pfree_bits = 0;
 }
-__device__ __noinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+__device__ __forceinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
     TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
     unsigned char* ring = smem + TC_OFF_RING;
     const TcStep S = tb->steps[st];
+#pragma unroll 1
     for (int c = 0; c < S.nchunks; ++c, ++cc) {
         const TcChunk ch = tb->chunks[S.chunk0 + c];
         const uint32_t s = cc % TC_NRING;
@@ -516,16 +585,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     const int n_pairs = (n_tiles + TC_TILES - 1) / TC_TILES;
     tc_setup(smem, sh, A.tab, TC_TILES);
 
-    if (warp == TC_TILES * 8) {
+    // Register re-balancing (setmaxnreg, per warpgroup): 20 warps are launched at 96 registers so that the register
+    // file of every SM sub-partition (5 warps x 32 x 96 <= 16 K) holds them; the last warpgroup (producer + 3 parked
+    // warps) shrinks to 24 and the 16 tile warps grow to 112, which is what the epilogues need to stay out of local memory.
+    if (warp >= TC_TILES * 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
         // ===================================================== weight producer
-        if (lane == 0) {
+        if (warp == TC_TILES * 8 && lane == 0) {
             uint32_t cc = 0;
 #pragma unroll 1
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+                if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;        // a bounded wait gave up: drain
 #pragma unroll 1
                 for (int v = 0; v < V; ++v)
 #pragma unroll 1
-                    for (int st = ST_G1; st <= ST_M3; ++st) tc_load_step(st, cc, smem, A.wblob);
+                    for (int st = ST_G1; st <= ST_M3; ++st)
+                        if (st != ST_G2) tc_load_step(st, cc, smem, A.wblob);       // attention layer 2 runs in registers
 #pragma unroll 1
                 for (int st = ST_Q1; st <= ST_Q3; ++st) tc_load_step(st, cc, smem, A.wblob);
 #pragma unroll 1
@@ -539,6 +614,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
         }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
         // ===================================================== tile threads
         TcTile t;
         tc_tile_init(t, smem, sh, warp, lane);
@@ -560,33 +636,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
                 if (leader) {          // all MMAs that read slots 0..3 have completed (last wait_acc)
                     tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], 4 * TC_SLOT);
+#pragma unroll 1
                     for (int s = 0; s < 4; ++s) tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
                 }
                 const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
-                const float pw = a1.w;
-                tc_prof(5000 + v);
+                const float pw = reinterpret_cast<const float*>(aux_row + v * TC_AUX_BYTES)[7];
+                TC_PROF(5000 + v);
                 tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 400);
                 t.rec_phase ^= 1;
-                tc_prof(5100 + v);
-                // ---- G1: attention layer 1 of both scales
+                TC_PROF(5100 + v);
+                // ---- G1: attention layer 1 of both scales -> acc cols 0..15 (scale 64), 16..31 (scale 8)
                 t.step(ST_G1);
-                if (h == 0) EPI(TA_RELU, 0, 1, NOBIAS, 3, 6);
-                else EPI(TA_RELU, 16, 1, NOBIAS, 4, 0);
-                // ---- G2: attention layer 2 -> sigmoid gates, applied in place
-                t.step(ST_G2);
+                // ---- attention layer 2 (10 -> 3, twice) + sigmoid in registers (fp32 weights), gates applied in place
                 {
-                    float g64[8], g8[8];
-                    t.ld8(0, g64);
-                    t.ld8(16, g8);
+                    float hid[16];
+                    float g64[3], g8[3];
+                    t.ld16(0, hid);
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) { g64[i] = tc_act<TA_SIGMOID>(g64[i]); g8[i] = tc_act<TA_SIGMOID>(g8[i]); }
+                    for (int j = 0; j < 3; ++j) {
+                        const float* w = t.tb->at2 + j * 12;
+                        float s = 0.0f;
 #pragma unroll
-                    for (int s = 0; s < 3; ++s)
+                        for (int i = 0; i < 10; ++i) s = fmaf(w[i], fmaxf(hid[i], 0.0f), s);
+                        g64[j] = tc_act<TA_SIGMOID>(s);
+                    }
+                    t.ld16(16, hid);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g64[s]);
-                    if (h == 0) t.gate_chunk1(3, 2, g8[0]);
-                    else { t.gate_chunk1(3, 3, g8[1]); t.gate_chunk1(3, 4, g8[2]); }
+                    for (int j = 0; j < 3; ++j) {
+                        const float* w = t.tb->at2 + 36 + j * 12;
+                        float s = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) s = fmaf(w[i], fmaxf(hid[i], 0.0f), s);
+                        g8[j] = tc_act<TA_SIGMOID>(s);
+                    }
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const uint32_t g2 = tc_dup_bf16(g64[s]);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g2);
+                    }
+                    if (h == 0) t.gate_chunk1(3, 2, tc_dup_bf16(g8[0]));
+                    else { t.gate_chunk1(3, 3, tc_dup_bf16(g8[1])); t.gate_chunk1(3, 4, tc_dup_bf16(g8[2])); }
                 }
                 // ---- G3: fused layer 1 (ReLU)
                 t.step(ST_G3);
@@ -603,16 +693,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     const int ps = s % 3;
                     const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : 4;
                     if (s >= 3) {
-                        tc_wait(&sh->pfree[tg][ps], t.pfree_phase[ps], sh->abort_flag, 500 + s);
-                        t.pfree_phase[ps] ^= 1;
+                        tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + s);
+                        t.pfree_bits ^= 1u << ps;
                     }
                     const int nk = s < 5 ? 4 : 1;
 #pragma unroll 1
                     for (int j = 0; j < nk; ++j) {
                         const int kp = 8 * s + 2 * j + h;
-                        const float* kc = t.tb->kpt + (v * NKPT + kp) * 3;
-                        const float dx = a0.x - kc[0], dy = a0.y - kc[1], dz = a0.z - kc[2];
-                        const float w = __expf(-(dx * dx + dy * dy + dz * dz) * 50.0f);       // exp(-d^2 / (2 * 0.1^2))
+                        const float4 kc = reinterpret_cast<const float4*>(t.tb->kpt4)[v * NKPT + kp];
+                        const float dx = a0.x - kc.x, dy = a0.y - kc.y, dz = a0.z - kc.z;
+                        const float w = tc_ex2((dx * dx + dy * dy + dz * dz) * -72.1347520f);   // exp(-d^2 / (2 * 0.1^2))
                         float s1, c1;
                         __sincosf(3.14159274f * dz, &s1, &c1);
                         const float s2 = 2.0f * s1 * c1, c2 = 1.0f - 2.0f * s1 * s1;
@@ -627,8 +717,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 // drain the ring-slot barriers committed by P3, P4 (slots 0, 1): already complete (MMAs complete in order)
 #pragma unroll 1
                 for (int ps = 0; ps < 2; ++ps) {
-                    tc_wait(&sh->pfree[tg][ps], t.pfree_phase[ps], sh->abort_flag, 510 + ps);
-                    t.pfree_phase[ps] ^= 1;
+                    tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 510 + ps);
+                    t.pfree_bits ^= 1u << ps;
                 }
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP0) + 64 * h, 1 + h, 0);        // h0 -> slots 1, 2
                 t.step(ST_M1);
@@ -643,11 +733,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     float x[16], s1[16], s2[16];
                     t.ld16(c0, x);
                     if (v > 0) { t.ld16(TC_SREG + c0, s1); t.ld16(TC_SREG + 64 + c0, s2); }
+                    const float* b3 = BIASP(L_MLP3) + c0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float hv = x[i] + BIASP(L_MLP3)[c0 + i];
-                        s1[i] = (v > 0 ? s1[i] : 0.0f) + pw * hv;
-                        s2[i] = (v > 0 ? s2[i] : 0.0f) + pw * hv * hv;
+                        const float hv = x[i] + b3[i];
+                        const float wh = pw * hv;
+                        s1[i] = (v > 0 ? s1[i] : 0.0f) + wh;
+                        s2[i] = fmaf(wh, hv, v > 0 ? s2[i] : 0.0f);
                     }
                     t.st16(TC_SREG + c0, s1);
                     t.st16(TC_SREG + 64 + c0, s2);
@@ -709,10 +801,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], TC_SLOT);
                     tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
                 }
-                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
                 // tail operand [lat24 | extras 8] in slot 2, ray difference (4) in slot 3 cols 0..15
                 if (h == 0) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
+                    const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
                     t.st_chunk(2, 0, lat_a);
                     t.st_chunk(2, 1, lat_b);
                     t.st_chunk(3, 0, make_uint4(tc::pack_bf16(a0.w, a1.x), tc::pack_bf16(a1.y, a1.z), 0, 0));
@@ -721,10 +813,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     t.st_chunk(2, 2, lat_a);
                     t.st_chunk(2, 3, *reinterpret_cast<const uint4*>(aux_row + v * TC_AUX_BYTES + 48));
                 }
-                tc_prof(5200 + v);
+                TC_PROF(5200 + v);
                 tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 401);
                 t.rec_phase ^= 1;
-                tc_prof(5300 + v);
+                TC_PROF(5300 + v);
                 // ---- T1: attention layer 1 (ReLU) + ray encoder layer 1 (ELU)
                 t.step(ST_T1);
                 if (h == 0) {
@@ -739,20 +831,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 {
                     float gt[8];
                     t.ld8(0, gt);
+                    uint32_t g2[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) gt[i] = tc_act<TA_SIGMOID>(gt[i]);
+                    for (int i = 0; i < 6; ++i) { gt[i] = tc_act<TA_SIGMOID>(gt[i]); g2[i] = tc_dup_bf16(gt[i]); }
                     // slot 1 chunks: 0 -> g0, 1 -> g1, 2 -> g2, 3,4 -> g3, 5,6 -> g4, 7 -> [g3,g3,g4,g4,g0,g0,g0,g1]
                     // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (kTexMap1 / kTexMap2)
                     if (h == 0) {
-                        t.gate_chunk1(1, 0, gt[0]); t.gate_chunk1(1, 1, gt[1]); t.gate_chunk1(1, 2, gt[2]); t.gate_chunk1(1, 3, gt[3]);
-                        t.gate_chunk1(2, 0, gt[5]); t.gate_chunk1(2, 1, gt[5]);
+                        t.gate_chunk1(1, 0, g2[0]); t.gate_chunk1(1, 1, g2[1]); t.gate_chunk1(1, 2, g2[2]); t.gate_chunk1(1, 3, g2[3]);
+                        t.gate_chunk1(2, 0, g2[5]); t.gate_chunk1(2, 1, g2[5]);
                     } else {
-                        t.gate_chunk1(1, 4, gt[3]); t.gate_chunk1(1, 5, gt[4]); t.gate_chunk1(1, 6, gt[4]);
-                        const float g7[8] = {gt[3], gt[3], gt[4], gt[4], gt[0], gt[0], gt[0], gt[1]};
-                        t.gate_chunk(1, 7, g7);
-                        t.gate_chunk1(2, 2, gt[5]);
-                        const float g3[8] = {gt[1], gt[1], gt[2], gt[2], gt[2], 1.0f, 1.0f, 1.0f};
-                        t.gate_chunk(2, 3, g3);
+                        t.gate_chunk1(1, 4, g2[3]); t.gate_chunk1(1, 5, g2[4]); t.gate_chunk1(1, 6, g2[4]);
+                        t.gate_chunk4(1, 7, g2[3], g2[4], g2[0], tc::pack_bf16(gt[0], gt[1]));
+                        t.gate_chunk1(2, 2, g2[5]);
+                        t.gate_chunk4(2, 3, g2[1], g2[2], tc::pack_bf16(gt[2], 1.0f), 0x3F803F80u);
                     }
                     const int fcol = TC_SREG + 40 * v;
                     if (h == 0) {
@@ -961,13 +1052,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     }
                 }
             }
-            tc_prof(6000);
+            TC_PROF(6000);
             // all TMEM reads of this tile precede the next tile's MMAs (ordered by the next step barrier)
+            // leave the loop as a group once a bounded wait has given up (a named barrier has no time-out: the decision
+            // must be the same for all 256 threads, so the leader takes it between two group barriers)
+            tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
+            if (leader) sh->stop[tg] = *reinterpret_cast<volatile int*>(sh->abort_flag);
+            tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
+            if (*reinterpret_cast<volatile int*>(&sh->stop[tg])) break;
         }
     }
     tc_teardown(sh, A.err);
 }
-
 // ================================================================================================ self test
 // D (128 x Npad, fp32) = bf16(A (128 x K)) * bf16(W (N x K))^T through the same slots / ring / issue / TMEM path as
 // k_mlp_tc, K <= 256 (multiple of 16), N <= 128.  c_tc holds a one-step table (index 0) built by tc_build_single.

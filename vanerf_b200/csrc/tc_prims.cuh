@@ -3,7 +3,7 @@
 // Spelling of the PTX follows the CUTLASS 4.x sm100 headers (cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp,
 // tmem_allocator_sm100.hpp, cutlass/arch/barrier.h); nothing here depends on CUTLASS.
 //
-// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_CYCLES raises the CTA-wide abort flag,
+// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_TRIES tries raises the CTA-wide abort flag,
 // after which all waits fall through, the kernel drains (garbage results), frees TMEM and the host reports an error.
 // A protocol bug therefore costs a wrong answer and an error code, never a hung GPU.
 #pragma once
@@ -12,7 +12,6 @@
 
 namespace tc {
 
-#define TC_WAIT_CYCLES 400000000ll        // ~0.2 s at 1.9 GHz
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -27,36 +26,33 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// One try_wait: suspends the warp in hardware until the phase completes or the suspend-time hint (ns) runs out, so a
+// waiting warp does not burn issue slots polling.
+#define TC_WAIT_HINT_NS 20000u
+#define TC_WAIT_TRIES 20000               // x hint = 0.4 s when the hint is honoured in full
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(TC_WAIT_HINT_NS)
         : "memory");
     return ok != 0;
 }
-// Returns false when the wait was abandoned (abort flag raised by this or another thread).  abort_flag[0] = code of
-// the first wait that gave up, abort_flag[1 + code / 100] = last code of each wait class that was still pending.
+// Returns false when the wait was abandoned (try budget spent, or the abort flag raised by another thread).
+// abort_flag[0] = code of the first wait that gave up, abort_flag[1 + code / 100] = last code of each wait class that
+// was still pending.  No clock and no call: the bound is a try count, so a wait site costs one loop counter.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
-    if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    for (;;) {
 #pragma unroll 1
-        for (int i = 0; i < 64; ++i)
-            if (mbar_try_wait(bar, parity)) return true;
-        if (*abort_flag) {
-            abort_flag[1 + code / 100] = code;
-            return false;
-        }
-        if (clock64() - t0 > TC_WAIT_CYCLES) {
-            if (*abort_flag == 0) *abort_flag = code;
-            abort_flag[1 + code / 100] = code;
-            return false;
-        }
+    for (int it = 0; it < TC_WAIT_TRIES; ++it) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if (*abort_flag) break;           // only reached when a try timed out (>= the hint), i.e. off the fast path
     }
+    if (*abort_flag == 0) *abort_flag = code;
+    abort_flag[1 + code / 100] = code;
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------------- proxies / fences
@@ -65,6 +61,9 @@ __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.f
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------- bulk copy (global -> smem)

@@ -197,10 +197,10 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
 #ifndef VANERF_HOST_EMUL
     {   // tensor-core path: step tables + swizzled bf16 weight images
         std::vector<uint16_t> img;
-        float kpt_keep[TC_MAXV * NKPT * 3];
-        memcpy(kpt_keep, ctx->h_tc.kpt, sizeof(kpt_keep));
+        float kpt_keep[TC_MAXV * NKPT * 4];
+        memcpy(kpt_keep, ctx->h_tc.kpt4, sizeof(kpt_keep));
         tc_build(src, w->ani_al, ctx->h_tc, img);
-        memcpy(ctx->h_tc.kpt, kpt_keep, sizeof(kpt_keep));
+        memcpy(ctx->h_tc.kpt4, kpt_keep, sizeof(kpt_keep));
         ctx->tc_tab_dirty = true;
         ENSURE(ctx, ctx->tcw, img.size() * 2);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tcw.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -290,8 +290,9 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
                   (float*)ctx->T64.p, (float*)ctx->T8.p, (float*)ctx->Ttex.p); CHECK_LAUNCH(ctx);
 #ifndef VANERF_HOST_EMUL
     {   // bf16 companions for the tensor-core path; camera-space keypoints go to the constant tables
-        memset(ctx->h_tc.kpt, 0, sizeof(ctx->h_tc.kpt));
-        memcpy(ctx->h_tc.kpt, kc.data(), sizeof(float) * std::min<size_t>(kc.size(), (size_t)TC_MAXV * NKPT * 3));
+        memset(ctx->h_tc.kpt4, 0, sizeof(ctx->h_tc.kpt4));
+        for (size_t i = 0; i < std::min<size_t>(kc.size() / 3, (size_t)TC_MAXV * NKPT); ++i)
+            for (int j = 0; j < 3; ++j) ctx->h_tc.kpt4[4 * i + j] = kc[3 * i + j];
         ctx->tc_tab_dirty = true;
         const size_t t64n = (size_t)V * Nv * 64, t8n = (size_t)V * Nv * 8, ttn = (size_t)V * Nv * 32;
         ENSURE(ctx, ctx->geo0b, g0n * 2); ENSURE(ctx, ctx->geo1b, g1n * 2); ENSURE(ctx, ctx->texb, txn * 2);
@@ -476,7 +477,7 @@ int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const flo
 // Cycle trace of CTA 0 / thread 0 of the next k_mlp_tc launches: buf dev (capacity, 2) int64 pairs (tag, clock64), NULL = off.
 // Returns the number of pairs recorded so far (after a stream synchronise) when buf == NULL.
 int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity) {
-#ifndef VANERF_HOST_EMUL
+#if !defined(VANERF_HOST_EMUL) && defined(VANERF_TC_TRACE)
     if (!ctx) return VANERF_ERR_INVALID;
     int n = 0, zero = 0;
     if (!buf) {
@@ -487,7 +488,7 @@ int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity) {
         cudaMemcpyToSymbol(d_tc_prof_n, &zero, sizeof(int)) != cudaSuccess) return VANERF_ERR_CUDA;
     return n;
 #else
-    (void)ctx; (void)buf; (void)capacity;
+    (void)ctx; (void)buf; (void)capacity;          // trace support is compiled in with -DVANERF_TC_TRACE only
     return 0;
 #endif
 }
