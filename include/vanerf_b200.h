@@ -191,6 +191,11 @@ int vanerf_tc_error(vanerf_ctx* ctx);
  * buf dev (capacity, 2) int64; buf == NULL switches the trace off and returns the number of pairs recorded. */
 int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity);
 int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host, int32_t K, int32_t N, float* D_dev, void* stream);
+/* 0 when the weight-packing script and the compile-time MMA program of the tensor-core kernels agree (CPU only). */
+int vanerf_tc_program_check(void);
+/* Developer measurement: cycles to issue / to complete `reps` tcgen05.mma of shape 128 x n x 16 round-robin over n_acc
+ * accumulators (mode bit 0: two issuing warps per CTA); out_host (2, 2) int64 = per warp [issue, total] of CTA 0. */
+int vanerf_tc_mma_probe(vanerf_ctx* ctx, int32_t n, int32_t reps, int32_t n_acc, int32_t mode, int32_t n_ctas, long long* out_host);
 
 /* Number of kernels launched by this context since creation (for bench.py's gpu_launches). */
 int64_t vanerf_launch_count(const vanerf_ctx* ctx);

@@ -37,6 +37,14 @@ def build_cuda(force=False, verbose=False):
     return CUDA_SO
 
 
+def build_trace(force=True):
+    """Developer build with the in-kernel cycle trace of k_mlp_tc compiled in (tools/tc_trace.py); not the product."""
+    out = os.path.join(ROOT, "vanerf_b200", "libvanerf_b200_trace.so")
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DVANERF_TC_TRACE",
+                           "-Xcompiler", "-fPIC", "-shared", "-o", out, os.path.join(CSRC, "vanerf_b200.cu")])
+    return out
+
+
 def build_emul(force=False):
     if not force and not _stale(EMUL_SO):
         return EMUL_SO
@@ -56,4 +64,4 @@ def build_oracle(force=False):
 if __name__ == "__main__":
     what = sys.argv[1:] or ["cuda", "oracle", "emul"]
     for w in what:
-        print(w, "->", {"cuda": build_cuda, "oracle": build_oracle, "emul": build_emul}[w](force=True))
+        print(w, "->", {"cuda": build_cuda, "oracle": build_oracle, "emul": build_emul, "trace": build_trace}[w](force=True))

@@ -38,22 +38,28 @@ torch.cuda.synchronize()
 n = r.lib.dll.vanerf_tc_profile(r.ctx, None, 0)
 t = buf[:n].cpu().numpy()
 print(f"shade of {n_rays * 64} samples ({n_rays * 64 // 128} tiles): {ev0.elapsed_time(ev1):.3f} ms, {n} trace points, tc_error {r.tc_error()}")
-t0 = t[0, 1]
-agg = {}
-prev = t0
-for tag, clk in t:
-    kind, st = divmod(int(tag), 1000)
-    name = {1: "epi_done", 2: "published", 3: "issued", 4: "acc_ready", 5: "rec", 6: "tile_end", 7: "fine"}.get(kind, "?")
-    if kind == 7:
-        name = {0: "f:before_wfull", 100: "f:wfull_ok", 200: "f:mma_issued", 300: "f:committed", 400: "f:epi_enter", 500: "f:ld_done", 600: "f:group_done"}.get(st, "f?")
-    label = f"{name}:{STEPS[st] if kind in (1, 2, 3, 4) and st < len(STEPS) else st}"
-    d = int(clk - prev)
-    agg.setdefault(name, [0, 0])
-    agg[name][0] += d
-    agg[name][1] += 1
-    print(f"{int(clk - t0):9d} +{d:7d}  {label}")
-    prev = clk
-print("total cycles", int(t[-1, 1] - t0))
-print("time attributed to the interval ENDING at each kind of marker:")
-for k, (c, m) in agg.items():
-    print(f"  {k:10s} {c:9d} cycles over {m} intervals")
+names = {1: "epi_done", 2: "fenced", 3: "issued", 4: "acc_ready", 5: "rec", 6: "tile_end", 7: "wfull", 8: "I:wait_ops", 9: "I:ops_ready"}
+for who, title in ((0, "tile thread 0"), (1, "issuer of tile 0")):
+    tt = [(int(tag) % 100000, int(clk)) for tag, clk in t if int(tag) // 100000 == who]
+    if not tt:
+        continue
+    print(f"==== {title}: {len(tt)} points")
+    t0 = tt[0][1]
+    prev = t0
+    agg = {}
+    for tag, clk in tt:
+        kind, st = divmod(tag, 1000)
+        name = names.get(kind, "?")
+        if kind == 7:
+            name = "wfull_wait" if st == 0 else "wfull_ok"
+        label = f"{name}:{STEPS[st] if kind in (1, 2, 3, 4, 8, 9) and st < len(STEPS) else st}"
+        d = clk - prev
+        agg.setdefault(name, [0, 0])
+        agg[name][0] += d
+        agg[name][1] += 1
+        print(f"{clk - t0:9d} +{d:7d}  {label}")
+        prev = clk
+    print("total cycles", tt[-1][1] - t0)
+    print("time attributed to the interval ENDING at each kind of marker:")
+    for k, (c, m) in agg.items():
+        print(f"  {k:12s} {c:9d} cycles over {m} intervals")

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvanerf_b200.so")
+# VANERF_B200_LIB: developer override (e.g. the cycle-trace build tools/build.py trace makes); same ABI, same kernels
+LIB_PATH = os.environ.get("VANERF_B200_LIB") or os.path.join(_HERE, "libvanerf_b200.so")
 
 MAX_VIEWS = 4
 RAY_STRIDE = 8
@@ -74,6 +75,8 @@ PROTOTYPES = {
     "vanerf_tc_error": (C.c_int, [_P]),
     "vanerf_tc_profile": (C.c_int, [_P, _P, _I]),
     "vanerf_tc_selftest": (C.c_int, [_P, _P, _P, _I, _I, _P, _P]),
+    "vanerf_tc_mma_probe": (C.c_int, [_P, _I, _I, _I, _I, _I, _P]),
+    "vanerf_tc_program_check": (C.c_int, []),
 }
 
 

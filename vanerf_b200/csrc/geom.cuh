@@ -75,11 +75,13 @@ __device__ __forceinline__ float aabb_dist2(const float4& mn, const float4& mx, 
     return dx * dx + dy * dy + dz * dz;
 }
 
-__device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p, float& best_d, int& best_f) {
+// bound_d: an upper bound of the result (squared distance to any mesh vertex, slightly inflated by the caller) or +inf.
+// It only prunes: the first-minimum face is still found and its distance is the one point_tri_dist2 computes.
+__device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p, float bound_d, float& best_d, int& best_f) {
     int stack[BVH_STACK];
     int sp = 0;
     stack[sp++] = 0;
-    best_d = __int_as_float(0x7f800000);
+    best_d = bound_d;
     best_f = 0x7fffffff;
     while (sp > 0) {
         const int ni = stack[--sp];
@@ -148,7 +150,7 @@ __device__ __forceinline__ bool inside_parity(const FrameDev& fr, const float* p
     return (cnt & 1) != 0;
 }
 
-__device__ __forceinline__ int nearest_vertex(const FrameDev& fr, const float* p) {
+__device__ __forceinline__ int nearest_vertex(const FrameDev& fr, const float* p, float& best_d_out) {
     int stack[BVH_STACK];
     int sp = 0;
     stack[sp++] = 0;
@@ -174,6 +176,7 @@ __device__ __forceinline__ int nearest_vertex(const FrameDev& fr, const float* p
             else { stack[sp++] = a; stack[sp++] = b; }
         }
     }
+    best_d_out = best_d;
     return best_i;
 }
 
@@ -214,15 +217,21 @@ __global__ void k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict
     if (pts_in) { p[0] = pts_in[3 * n]; p[1] = pts_in[3 * n + 1]; p[2] = pts_in[3 * n + 2]; }
     else sample_point(rays + (size_t)r * VANERF_RAY_STRIDE, tar.cam_pos, z[n], p);
     if (pts) { pts[3 * n] = p[0]; pts[3 * n + 1] = p[1]; pts[3 * n + 2] = p[2]; }
+    // nearest vertex first: its squared distance bounds the closest-face distance from above (the vertex belongs to a
+    // face), which prunes most of the triangle traversal.  Inflated by 1e-4 relative so that rounding differences
+    // between the two distance formulas (~1e-6) cannot exclude the true closest face.
+    float dnn2;
+    const int nnv = nearest_vertex(fr, p, dnn2);
     float d2; int f;
-    closest_face(fr, p, d2, f);
+    closest_face(fr, p, dnn2 * 1.0001f + 1e-12f, d2, f);
+    if (f == 0x7fffffff) closest_face(fr, p, __int_as_float(0x7f800000), d2, f);     // never expected; keeps the result exact
     const bool in = inside_parity(fr, p);
     // pts_sdf = sqrt(d2 + 1e-6) * (-2 * (inside - 0.5))   (mesh_util.py:510-512)
     const float dist = xsqrt(xadd(d2, 1e-6f));
     const float sign = xmul(-2.0f, xsub(in ? 1.0f : 0.0f, 0.5f));
     if (sdf) sdf[n] = xmul(dist, sign);
     if (face) face[n] = f;
-    if (nn_vert) nn_vert[n] = nearest_vertex(fr, p);
+    if (nn_vert) nn_vert[n] = nnv;
     if (qvis) {
         float bw[3];
         bary_of_projection(fr, p, f, bw);

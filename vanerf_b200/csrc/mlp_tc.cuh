@@ -27,9 +27,10 @@
 #define TC_NRING 3
 #define TC_TILES 2                       // tiles in flight per CTA
 #define TC_EPI_THREADS 256               // threads of one tile group
-#define TC_THREADS (TC_TILES * TC_EPI_THREADS + 128)   // + one warpgroup: weight producer warp and three parked warps
+#define TC_THREADS (TC_TILES * TC_EPI_THREADS + 128)   // + one warpgroup: weight producer warp, one MMA issuer warp per tile, one parked warp
 #define TC_REGS_EPI 112                  // registers of a tile thread after setmaxnreg (kernel is compiled for 96)
-#define TC_REGS_PROD 24                  // registers of the producer warpgroup (gives 72 x 128 back to the pool)
+#define TC_REGS_PROD 32                  // registers of the producer / issuer warpgroup (gives 64 x 128 back to the pool)
+#define TC_NREADY 4                      // operand-ready barriers per tile: a warp runs at most 3 steps ahead of the slowest (PE ring)
 #define TC_TMEM_COLS 512
 #define TC_TMEM_TILE 256                 // TMEM columns per tile
 #define TC_SREG 128                      // TMEM columns of the pooling sums S1|S2, later the per-view f (40 each)
@@ -37,11 +38,11 @@
 #define TC_MAXV 3
 #define TC_OFF_RING (TC_TILES * TC_NACT * TC_SLOT)
 #define TC_OFF_TAB (TC_OFF_RING + TC_NRING * TC_SLOT)
-#define TC_TAB_BYTES 9216                // >= sizeof(TcTables), multiple of 16
+#define TC_TAB_BYTES 6656                // >= sizeof(TcTables), multiple of 16
 #define TC_OFF_CTRL (TC_OFF_TAB + TC_TAB_BYTES)
 #define TC_OFF_TRACE (TC_OFF_CTRL + 512)
 #ifdef VANERF_TC_TRACE
-#define TC_TRACE_N 1024                   // cycle-trace entries (tag << 48 | clock), developer aid
+#define TC_TRACE_N 1024                   // cycle-trace entries (tag << 48 | clock), developer aid: 512 per traced thread
 #else
 #define TC_TRACE_N 0
 #endif
@@ -67,14 +68,111 @@ struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_BIAS 1024
 struct TcTables {                        // global memory (context-owned); copied to shared memory once per CTA
     alignas(16) float bias[TC_MAX_BIAS]; // read as float4 (offsets are multiples of 16 floats)
-    TcStep steps[ST_COUNT];
-    TcOp ops[TC_MAX_OPS];
-    TcChunk chunks[TC_MAX_CHUNKS];
     alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
     alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
 };
+// The static MMA program (depends on the layer shapes only).  It lives in __constant__ memory: the issuing warp reads
+// it with uniform loads, so operand descriptors are formed in uniform registers and tcgen05.mma issues back to back.
+struct TcProg {
+    TcStep steps[ST_COUNT];
+    TcOp ops[TC_MAX_OPS];
+    TcChunk chunks[TC_MAX_CHUNKS];
+    uint16_t cc_off[ST_COUNT];           // weight chunks that precede the step inside one iteration of its group
+    uint16_t cc_gm, cc_q, cc_t, cc_i;    // chunks per iteration of: geometry+MLP (per view, ST_G2 excluded), density head,
+                                         // texture fusion (per view), rendering head (per view)
+};
+
+// ---- compile-time copy of the program --------------------------------------------------------------------------
+// The layer shapes are fixed (configs/vanerf.json, checked by vanerf_load_weights), so the step / op / chunk tables are
+// known at compile time.  kProg is what the MMA issuer warps execute: every descriptor offset, accumulator column and
+// instruction descriptor becomes an immediate, and issuing a step costs no table loads.  The host builds the same
+// tables again from the packing script (tc_build, which also produces the weight images) and tc_program_matches()
+// refuses to run if the two ever disagree.
+struct TcSpecC { int step, layer, slot, col0, d_col, accum, ncols; };
+constexpr int kLayerOut[L_COUNT] = {10, 3, 64, 64, 10, 3, 8, 8, 128, 128, 120, 64, 64, 64, 2, 24, 96, 6, 96, 40,
+                                    16, 40, 64, 32, 32, 33, 32, 1, 16, 8, 1};
+constexpr TcSpecC kSpecs[] = {
+    {ST_G1, L_GEO_AT0, 0, 0, 0, 0, 64}, {ST_G1, L_GEO_AT0, 1, 0, 0, 1, 64}, {ST_G1, L_GEO_AT0, 2, 0, 0, 1, 64}, {ST_G1, L_GEO_AT0, 3, 0, 0, 1, 16},
+    {ST_G1, L_GEO8_AT0, 3, 16, 16, 0, 32},
+    {ST_G2, L_GEO_AT1, 3, 48, 0, 0, 16}, {ST_G2, L_GEO8_AT1, 4, 0, 16, 0, 16},
+    {ST_G3, L_GEO_F0, 0, 0, 0, 0, 64}, {ST_G3, L_GEO_F0, 1, 0, 0, 1, 64}, {ST_G3, L_GEO_F0, 2, 0, 0, 1, 64}, {ST_G3, L_GEO_F0, 3, 0, 0, 1, 16},
+    {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32},
+    {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16},
+    {ST_M0, L_MLP0, 0, 0, 0, 0, 64},
+    {ST_P0, L_MLP0, 1, 0, 0, 1, 64}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64}, {ST_P2, L_MLP0, 4, 0, 0, 1, 64},
+    {ST_P3, L_MLP0, 1, 0, 0, 1, 64}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64}, {ST_P5, L_MLP0, 4, 0, 0, 1, 16},
+    {ST_M1, L_MLP1, 1, 0, 0, 0, 64}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64},
+    {ST_M2, L_MLP2, 4, 0, 0, 0, 64}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16},
+    {ST_M3, L_MLP3, 1, 0, 0, 0, 64}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64},
+    {ST_Q1, L_POST0, 1, 0, 0, 0, 64}, {ST_Q1, L_POST0, 2, 0, 0, 1, 64}, {ST_Q1, L_COMPRESS, 1, 0, 64, 0, 64}, {ST_Q1, L_COMPRESS, 2, 0, 64, 1, 64},
+    {ST_Q2, L_POST1, 4, 0, 0, 0, 64},
+    {ST_Q3, L_POST2, 0, 0, 0, 0, 64},
+    {ST_T1, L_TEX_AT0, 1, 0, 0, 0, 64}, {ST_T1, L_TEX_AT0, 2, 0, 0, 1, 32}, {ST_T1, L_RAY0, 3, 0, 96, 0, 16},
+    {ST_T2, L_TEX_AT1, 4, 0, 0, 0, 64}, {ST_T2, L_TEX_AT1, 0, 0, 0, 1, 32}, {ST_T2, L_RAY1, 3, 16, 16, 0, 16},
+    {ST_T3, L_TEX_F0, 1, 0, 0, 0, 64}, {ST_T3, L_TEX_F0, 2, 0, 0, 1, 32},
+    {ST_T4, L_TEX_F1, 4, 0, 0, 0, 64}, {ST_T4, L_TEX_F1, 0, 0, 0, 1, 32},
+    {ST_I1, L_BASE0, 1, 0, 0, 0, 64}, {ST_I1, L_BASE0, 2, 0, 0, 1, 64},
+    {ST_I2, L_BASE1, 4, 0, 0, 0, 64},
+    {ST_I3, L_VIS1_0, 0, 0, 0, 0, 32}, {ST_I4, L_VIS1_1, 0, 32, 0, 0, 32}, {ST_I5, L_VIS2_0, 0, 0, 0, 0, 32}, {ST_I6, L_VIS2_1, 0, 32, 0, 0, 32},
+    {ST_I7, L_OUT0, 3, 0, 0, 0, 48}, {ST_I8, L_OUT1, 3, 48, 0, 0, 16}, {ST_I9, L_OUT2, 0, 0, 0, 0, 16},
+};
+constexpr int kNumSpecs = (int)(sizeof(kSpecs) / sizeof(kSpecs[0]));
+
+constexpr TcProg tc_make_prog() {
+    TcProg P{};
+    int n_ops = 0, n_chunks = 0;
+    uint32_t blob_bytes = 0;
+    for (int s = 0; s < ST_COUNT; ++s) {
+        P.steps[s].op0 = (uint16_t)n_ops;
+        P.steps[s].chunk0 = (uint16_t)n_chunks;
+        uint32_t cur_bytes = 0;
+        int rel = -1;
+        for (int q = 0; q < kNumSpecs; ++q) {
+            if (kSpecs[q].step != s) continue;
+            const int n_pad = (kLayerOut[kSpecs[q].layer] + 15) & ~15;
+            const uint32_t bytes = (uint32_t)n_pad * 128;
+            if (rel < 0 || cur_bytes + bytes > TC_SLOT) {
+                if (rel >= 0) P.ops[n_ops - 1].last_in_chunk = 1;
+                ++rel;
+                P.chunks[n_chunks].src_off = blob_bytes;
+                P.chunks[n_chunks].bytes = 0;
+                ++n_chunks;
+                cur_bytes = 0;
+            }
+            P.ops[n_ops].a_off = (uint32_t)(kSpecs[q].slot * TC_SLOT + (kSpecs[q].col0 / 16) * 32);
+            P.ops[n_ops].b_off = cur_bytes;
+            P.ops[n_ops].idesc = tc::umma_idesc_bf16(128, n_pad);
+            P.ops[n_ops].d_col = (uint16_t)kSpecs[q].d_col;
+            P.ops[n_ops].nk = (uint8_t)(kSpecs[q].ncols / 16);
+            P.ops[n_ops].accum = (uint8_t)kSpecs[q].accum;
+            P.ops[n_ops].chunk_rel = (uint8_t)rel;
+            P.ops[n_ops].last_in_chunk = 0;
+            ++n_ops;
+            cur_bytes += bytes;
+            blob_bytes += bytes;
+            P.chunks[n_chunks - 1].bytes = cur_bytes;
+        }
+        if (n_ops > P.steps[s].op0) P.ops[n_ops - 1].last_in_chunk = 1;
+        P.steps[s].nops = (uint16_t)(n_ops - P.steps[s].op0);
+        P.steps[s].nchunks = (uint16_t)(n_chunks - P.steps[s].chunk0);
+    }
+    const int grp_first[4] = {ST_G1, ST_Q1, ST_T1, ST_I1}, grp_last[4] = {ST_M3, ST_Q3, ST_T4, ST_I9};
+    for (int g = 0; g < 4; ++g) {
+        int acc = 0;
+        for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
+            P.cc_off[st] = (uint16_t)acc;
+            if (st != ST_G2) acc += P.steps[st].nchunks;
+        }
+        if (g == 0) P.cc_gm = (uint16_t)acc;
+        else if (g == 1) P.cc_q = (uint16_t)acc;
+        else if (g == 2) P.cc_t = (uint16_t)acc;
+        else P.cc_i = (uint16_t)acc;
+    }
+    return P;
+}
+constexpr TcProg kProg = tc_make_prog();
 
 // ================================================================================================ host: script + images
 struct TcOpSpec {
@@ -175,15 +273,16 @@ static inline uint16_t f2bf_host(float f) {
 }
 
 // Builds the step / op / chunk tables and the bf16 weight images (blob) from the folded fp32 layers.
-static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, std::vector<uint16_t>& blob) {
+static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, TcProg& P, std::vector<uint16_t>& blob) {
     std::vector<std::vector<TcOpSpec>> st;
     tc_build_script(st);
     memset(&T, 0, sizeof(T));
+    memset(&P, 0, sizeof(P));
     blob.clear();
     int n_ops = 0, n_chunks = 0;
     for (int s = 0; s < ST_COUNT; ++s) {
-        T.steps[s].op0 = (uint16_t)n_ops;
-        T.steps[s].chunk0 = (uint16_t)n_chunks;
+        P.steps[s].op0 = (uint16_t)n_ops;
+        P.steps[s].chunk0 = (uint16_t)n_chunks;
         uint32_t cur_bytes = 0;
         int rel = -1;
         for (const TcOpSpec& o : st[s]) {
@@ -192,14 +291,14 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
             const int ncols = (int)o.kmap.size();
             const uint32_t bytes = (uint32_t)n_pad * 128;
             if (rel < 0 || cur_bytes + bytes > TC_SLOT) {          // open a new chunk
-                if (rel >= 0) T.ops[n_ops - 1].last_in_chunk = 1;
+                if (rel >= 0) P.ops[n_ops - 1].last_in_chunk = 1;
                 ++rel;
-                T.chunks[n_chunks].src_off = (uint32_t)(blob.size() * 2);
-                T.chunks[n_chunks].bytes = 0;
+                P.chunks[n_chunks].src_off = (uint32_t)(blob.size() * 2);
+                P.chunks[n_chunks].bytes = 0;
                 ++n_chunks;
                 cur_bytes = 0;
             }
-            TcOp& d = T.ops[n_ops++];
+            TcOp& d = P.ops[n_ops++];
             d.a_off = (uint32_t)(o.a_slot * TC_SLOT + (o.a_col0 / 16) * 32);
             d.b_off = cur_bytes;
             d.idesc = tc::umma_idesc_bf16(128, n_pad);
@@ -218,11 +317,11 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
                     blob[base + byte / 2] = f2bf_host(L.w[(size_t)n * L.in_dim + ki]);
                 }
             cur_bytes += bytes;
-            T.chunks[n_chunks - 1].bytes = cur_bytes;
+            P.chunks[n_chunks - 1].bytes = cur_bytes;
         }
-        if (n_ops > T.steps[s].op0) T.ops[n_ops - 1].last_in_chunk = 1;
-        T.steps[s].nops = (uint16_t)(n_ops - T.steps[s].op0);
-        T.steps[s].nchunks = (uint16_t)(n_chunks - T.steps[s].chunk0);
+        if (n_ops > P.steps[s].op0) P.ops[n_ops - 1].last_in_chunk = 1;
+        P.steps[s].nops = (uint16_t)(n_ops - P.steps[s].op0);
+        P.steps[s].nchunks = (uint16_t)(n_chunks - P.steps[s].chunk0);
     }
     int boff = 0;
     for (int l = 0; l < L_COUNT; ++l) {
@@ -233,6 +332,18 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
         }
     }
     T.bias_off[L_COUNT] = (uint16_t)boff;
+    {   // chunk offsets of the steps inside their group (attention layer 2 of GeoVisFusion runs in registers: no ST_G2)
+        const int grp_first[4] = {ST_G1, ST_Q1, ST_T1, ST_I1}, grp_last[4] = {ST_M3, ST_Q3, ST_T4, ST_I9};
+        uint16_t* tot[4] = {&P.cc_gm, &P.cc_q, &P.cc_t, &P.cc_i};
+        for (int g = 0; g < 4; ++g) {
+            int acc = 0;
+            for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
+                P.cc_off[st] = (uint16_t)acc;
+                if (st != ST_G2) acc += P.steps[st].nchunks;
+            }
+            *tot[g] = (uint16_t)acc;
+        }
+    }
     T.ani_al_abs = fabsf(ani_al);
     for (int sc = 0; sc < 2; ++sc) {
         const vanerf_linear& L = *src[sc ? L_GEO8_AT1 : L_GEO_AT1];
@@ -241,7 +352,23 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
     }
 }
 
+// true when the tables the packing script produced are the ones the kernels were compiled with
+static bool tc_program_matches(const TcProg& P) {
+    static const TcProg K = kProg;
+    for (int s = 0; s < ST_COUNT; ++s)
+        if (P.steps[s].op0 != K.steps[s].op0 || P.steps[s].nops != K.steps[s].nops || P.steps[s].chunk0 != K.steps[s].chunk0 ||
+            P.steps[s].nchunks != K.steps[s].nchunks || P.cc_off[s] != K.cc_off[s]) return false;
+    for (int i = 0; i < TC_MAX_OPS; ++i)
+        if (P.ops[i].a_off != K.ops[i].a_off || P.ops[i].b_off != K.ops[i].b_off || P.ops[i].idesc != K.ops[i].idesc ||
+            P.ops[i].d_col != K.ops[i].d_col || P.ops[i].nk != K.ops[i].nk || P.ops[i].accum != K.ops[i].accum ||
+            P.ops[i].chunk_rel != K.ops[i].chunk_rel || P.ops[i].last_in_chunk != K.ops[i].last_in_chunk) return false;
+    for (int i = 0; i < TC_MAX_CHUNKS; ++i)
+        if (P.chunks[i].src_off != K.chunks[i].src_off || P.chunks[i].bytes != K.chunks[i].bytes) return false;
+    return P.cc_gm == K.cc_gm && P.cc_q == K.cc_q && P.cc_t == K.cc_t && P.cc_i == K.cc_i;
+}
+
 static_assert(sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
+static_assert(sizeof(TcProg) <= 8192, "TcProg must stay a small part of constant memory");
 // ================================================================================================ device
 // Optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile), compiled in only with -DVANERF_TC_TRACE: entries
 // (tag << 48 | clock64 & (2^48-1)) collected in shared memory and flushed to d_tc_prof when the kernel ends.
@@ -250,12 +377,16 @@ extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
 __device__ long long* d_tc_prof = nullptr;
 __device__ int d_tc_prof_cap = 0;
 __device__ int d_tc_prof_n = 0;
+// traced threads of CTA 0: thread 0 (tile 0, row 0) and lane 0 of tile 0's MMA issuer warp (tags + 100000)
+#define TC_TRACE_ISSUER (TC_TILES * TC_EPI_THREADS + 32)
 __device__ __forceinline__ void tc_prof(int tag) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        int* ctr = reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == TC_TRACE_ISSUER)) {
+        const int who = threadIdx.x == 0 ? 0 : 1;
+        int* ctr = reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 496 + 4 * who);
         const int i = *ctr;
-        if (i < 0 || i >= TC_TRACE_N) return;       // -1 = tracing off
-        reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[i] = ((unsigned long long)tag << 48) | ((unsigned long long)clock64() & 0xffffffffffffull);
+        if (i < 0 || i >= TC_TRACE_N / 2) return;       // -1 = tracing off
+        reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[who * (TC_TRACE_N / 2) + i] =
+            ((unsigned long long)(tag + 100000 * who) << 40) | ((unsigned long long)clock64() & 0xffffffffffull);
         *ctr = i + 1;
     }
 }
@@ -266,6 +397,7 @@ __device__ __forceinline__ void tc_prof(int tag) {
 
 struct TcShared {                      // control block behind the tables
     uint64_t wfull[TC_NRING], wempty[TC_NRING], acc_bar[TC_TILES], rec_bar[TC_TILES], pfree[TC_TILES][3];
+    uint64_t ready[TC_TILES][TC_NREADY];   // operands of step n published (8 arrivals: one per tile warp), n mod TC_NREADY
     uint32_t tmem_base;
     int abort_flag[8];                 // [0] first code that gave up, [1 + code/100] pending wait classes (tc_prims.cuh)
     int stop[TC_TILES];                // per tile group: leave the persistent loop (abort seen by the group's leader)
@@ -336,58 +468,100 @@ __device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile
     return tc::mbar_wait(bar, parity, abort_flag, code);
 }
 
-// Issues the MMAs of step `st` (one thread).  commit_to: 0 = accumulator barrier, 1..3 = PE ring-slot barrier
-// (commit_to - 1), -1 = none.  cc = running weight-chunk counter; the new value is returned.
-__device__ __forceinline__ uint32_t tc_issue_ops(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
-    const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
-    const uint32_t act_u32 = tc::smem_u32(smem) + tg * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(smem) + TC_OFF_RING;
-    const uint32_t tmem = sh->tmem_base + tg * TC_TMEM_TILE;
-    const TcStep S = tb->steps[st];
-    int cur = -1;
-    uint32_t slot_i = 0;
-#pragma unroll 1
-    for (int i = 0; i < S.nops; ++i) {
-        const TcOp op = tb->ops[S.op0 + i];
-        if ((int)op.chunk_rel != cur) {
-            cur = op.chunk_rel;
-            const uint32_t c = cc + cur;
-            slot_i = c % TC_NRING;
-            TC_PROF(7000);
-            tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
-            tc::tcgen05_fence_after();
-            TC_PROF(7100);
-        }
-        const uint64_t ad = tc::umma_desc_sw128(act_u32 + op.a_off);
-        const uint64_t bd = tc::umma_desc_sw128(ring_u32 + slot_i * TC_SLOT + op.b_off);
-#pragma unroll 1
+__constant__ TcProg c_prog;
+
+__device__ __forceinline__ bool tc_elect() {            // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Shared-memory matrix descriptor of the K-major 128B-swizzle layout, split: the high word is constant.
+#define TC_DESC_HI ((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29))
+__device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
+    return ((uint64_t)TC_DESC_HI << 32) | (uint64_t)(((smem_addr & 0x3FFFFu) >> 4) | (1u << 16));
+}
+
+// Issues op I (and the following ones) of step ST: everything but the ring slot of the weight chunk is an immediate.
+// Whole warp, converged; `lead` = the elected lane that executes the MMAs and commits.
+template <int ST, int I>
+__device__ __forceinline__ void tc_issue_op(uint32_t cc, uint32_t slot_i, TcShared* sh, uint32_t act_u32, uint32_t ring_u32,
+                                            uint32_t tmem, bool lead) {
+    constexpr TcStep S = kProg.steps[ST];
+    constexpr TcOp op = kProg.ops[S.op0 + I];
+    constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
+    if (first_in_chunk) {
+        const uint32_t c = cc + op.chunk_rel;
+        slot_i = c % TC_NRING;
+        TC_PROF(7000);
+        tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
+        tc::tcgen05_fence_after();
+        TC_PROF(7100);
+    }
+    // descriptors are formed outside the elected-lane branch so that they stay on the uniform datapath
+    const uint64_t ad = tc_desc(act_u32 + op.a_off);
+    const uint64_t bd = tc_desc(ring_u32 + slot_i * TC_SLOT + op.b_off);
+    if (lead) {
+#pragma unroll
         for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
             tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
-        TC_PROF(7200);
         if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
-        TC_PROF(7300);
     }
-    cc += S.nchunks;
-    if (commit_to == 0) tc::umma_commit(&sh->acc_bar[tg]);
-    else if (commit_to > 0) tc::umma_commit(&sh->pfree[tg][commit_to - 1]);
-    TC_PROF(3000 + st);              // MMAs issued (includes the wait for the weight chunk)
-    return cc;
+    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1>(cc, slot_i, sh, act_u32, ring_u32, tmem, lead);
 }
-// Publishes the calling threads' operand writes (and orders their TMEM reads before the coming MMAs), then the
-// tile's first thread issues the MMAs of step `st`.  All 256 threads of tile group `tg` call it and synchronise on the
-// tile's named barrier (a non-blocking arrive would let a fast warp lap the issuing warp in the PE steps, which have
-// no accumulator wait in between).
-__device__ __forceinline__ uint32_t tc_issue(int st, int commit_to, uint32_t cc, unsigned char* smem, int tg) {
-    TC_PROF(1000 + st);                  // epilogue of the previous step done (this thread)
-    tc::fence_proxy_async();
-    tc::tcgen05_fence_before();
-    tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
-    TC_PROF(2000 + st);                  // all operand writes published
-    if ((threadIdx.x & (TC_EPI_THREADS - 1)) == 0) {
-        tc::tcgen05_fence_after();
-        cc = tc_issue_ops(st, commit_to, cc, smem, tg);
+// One step of an MMA issuer warp: wait until the tile's eight warps have published the operands of step number n
+// (and finished reading the accumulators the step overwrites), then issue the step's MMAs and commit.
+// COMMIT: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (COMMIT - 1), -1 = none.
+// cc_base = index of the first weight chunk of this iteration of the step's group (see TcProg::cc_off).
+template <int ST, int COMMIT>
+__device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, TcShared* sh, uint32_t act_u32, uint32_t ring_u32,
+                                               uint32_t tmem, int tg, bool lead) {
+    TC_PROF(8000 + ST);                  // issuer: previous step issued, waiting for this step's operands
+    const bool ok = tc::mbar_wait(&sh->ready[tg][n % TC_NREADY], (n / TC_NREADY) & 1, sh->abort_flag, 600 + ST);
+    ++n;
+    tc::tcgen05_fence_after();
+    TC_PROF(9000 + ST);                  // issuer: operands ready
+    constexpr uint32_t cc_off = kProg.cc_off[ST];
+    // The operand addresses are tied to the outcome of the wait (+0 unless the wait was abandoned, in which case the
+    // kernel is draining and results are discarded): otherwise the compiler computes the descriptors of all 140-odd
+    // MMAs ahead of the waits and spills them to local memory.
+    const uint32_t never = ok ? 0u : 16u;
+    tc_issue_op<ST, 0>(cc_base + cc_off, 0, sh, act_u32 + never, ring_u32 + never, tmem, lead);
+    if (lead) {
+        if (COMMIT == 0) tc::umma_commit(&sh->acc_bar[tg]);
+        else if (COMMIT > 0) tc::umma_commit(&sh->pfree[tg][COMMIT > 0 ? COMMIT - 1 : 0]);
     }
-    return cc;
+    __syncwarp();
+    TC_PROF(3000 + ST);                  // MMAs issued (includes the wait for the weight chunk)
+}
+
+// Table-driven variant for the MMA self test (one step of arbitrary K, N read from __constant__ c_prog).
+__device__ __forceinline__ void tc_issue_ops_dyn(int st, uint32_t cc_base, TcShared* sh, uint32_t act_u32, uint32_t ring_u32, uint32_t tmem, int tg) {
+    const TcStep S = c_prog.steps[st];
+    const uint32_t cc = cc_base + c_prog.cc_off[st];
+    const bool lead = tc_elect();
+    uint32_t slot_i = 0;
+    int cur = -1;
+#pragma unroll 1
+    for (int i = 0; i < S.nops; ++i) {
+        const TcOp op = c_prog.ops[S.op0 + i];
+        if ((int)op.chunk_rel != cur) {
+            cur = op.chunk_rel;
+            const uint32_t c = cc + op.chunk_rel;
+            slot_i = c % TC_NRING;
+            tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + st);
+            tc::tcgen05_fence_after();
+        }
+        const uint64_t ad = tc_desc(act_u32 + op.a_off);
+        const uint64_t bd = tc_desc(ring_u32 + slot_i * TC_SLOT + op.b_off);
+        if (lead) {
+#pragma unroll 1
+            for (int k = 0; k < op.nk; ++k)
+                tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
+            if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
+        }
+    }
+    if (lead) tc::umma_commit(&sh->acc_bar[tg]);
+    __syncwarp();
 }
 
 struct TcTile {
@@ -398,7 +572,8 @@ struct TcTile {
     uint32_t trow;            // TMEM address of this thread's row, first column of this tile's half
     uint32_t row_off, rx;     // byte offset of this thread's row inside a slot, row & 7 (swizzle key)
     int row, half, tg;
-    uint32_t acc_phase, rec_phase, pfree_bits, cc;       // pfree_bits: bit ps = phase parity of PE ring slot ps
+    uint32_t acc_phase, rec_phase, pfree_bits;           // pfree_bits: bit ps = phase parity of PE ring slot ps
+    uint32_t step_n;                                     // number of steps signalled so far (selects the operand-ready barrier)
 
     __device__ __forceinline__ unsigned char* slot(int s) const { return act + s * TC_SLOT; }
     __device__ __forceinline__ uint32_t coff(int chunk) const { return row_off + (((uint32_t)chunk ^ rx) << 4); }
@@ -434,7 +609,20 @@ struct TcTile {
         for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
         tc::tmem_st8(trow + col, r);
     }
-    __device__ __forceinline__ void issue(int st, int commit_to) { cc = tc_issue(st, commit_to, cc, smem, tg); }
+    // Publishes the calling warp's operand writes (and orders its TMEM reads before the coming MMAs) and tells the
+    // tile's MMA issuer warp: one arrival per warp on the operand-ready barrier of this step number.  Non-blocking; a
+    // warp can be at most TC_NREADY - 1 steps ahead of the slowest warp of its tile (the PE steps have no accumulator
+    // wait in between, their ring-slot waits bound the lead to 3), so TC_NREADY barriers are never lapped.
+    __device__ __forceinline__ void issue(int st, int commit_to) {
+        (void)st; (void)commit_to;            // the issuer warp walks the same static sequence (TcProg::seq_*)
+        TC_PROF(1000 + st);                   // epilogue of the previous step done (this thread)
+        tc::fence_proxy_async();
+        TC_PROF(2000 + st);                   // proxy fence done
+        tc::tcgen05_fence_before();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&sh->ready[tg][step_n % TC_NREADY]);
+        ++step_n;
+    }
     __device__ __forceinline__ void wait_acc(int st) {
         tc_wait(&sh->acc_bar[tg], acc_phase, sh->abort_flag, 200 + st);
         acc_phase ^= 1;
@@ -507,12 +695,14 @@ __device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, cons
             tc::mbar_init(&sh->acc_bar[g], 1);
             tc::mbar_init(&sh->rec_bar[g], 1);
             for (int i = 0; i < 3; ++i) tc::mbar_init(&sh->pfree[g][i], 1);
+            for (int i = 0; i < TC_NREADY; ++i) tc::mbar_init(&sh->ready[g][i], TC_EPI_THREADS / 32);
         }
         for (int i = 0; i < 8; ++i) sh->abort_flag[i] = 0;
         for (int g = 0; g < TC_TILES; ++g) sh->stop[g] = 0;
         if ((tc::smem_u32(smem) & 1023u) != 0) sh->abort_flag[0] = 1;       // operand slots need 1024-byte alignment
 #ifdef VANERF_TC_TRACE
-        *reinterpret_cast<int*>(smem + TC_OFF_CTRL + 504) = (blockIdx.x == 0 && d_tc_prof != nullptr) ? 0 : -1;
+        for (int w = 0; w < 2; ++w)
+            *reinterpret_cast<int*>(smem + TC_OFF_CTRL + 496 + 4 * w) = (blockIdx.x == 0 && d_tc_prof != nullptr) ? 0 : -1;
 #endif
         tc::mbar_fence_init();
     }
@@ -534,20 +724,23 @@ __device__ __forceinline__ void tc_teardown(TcShared* sh, int* err) {
     if (tid == 0 && sh->abort_flag[0] && atomicCAS(err, 0, sh->abort_flag[0]) == 0)
         for (int i = 1; i < 8; ++i) err[i] = sh->abort_flag[i];
 #ifdef VANERF_TC_TRACE
-    if (tid == 0 && blockIdx.x == 0 && d_tc_prof) {             // flush the cycle trace
-        const int n = *reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 504);
+    if (tid == 0 && blockIdx.x == 0 && d_tc_prof) {             // flush the cycle traces
         int base = d_tc_prof_n;
-        for (int i = 0; i < n && base + i < d_tc_prof_cap; ++i) {
-            const unsigned long long e = reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[i];
-            d_tc_prof[2 * (base + i)] = (long long)(e >> 48);
-            d_tc_prof[2 * (base + i) + 1] = (long long)(e & 0xffffffffffffull);
+        for (int w = 0; w < 2; ++w) {
+            const int n = *reinterpret_cast<int*>(tc_smem_raw + TC_OFF_CTRL + 496 + 4 * w);
+            for (int i = 0; i < n && base < d_tc_prof_cap; ++i, ++base) {
+                const unsigned long long e = reinterpret_cast<unsigned long long*>(tc_smem_raw + TC_OFF_TRACE)[w * (TC_TRACE_N / 2) + i];
+                d_tc_prof[2 * base] = (long long)(e >> 40);
+                d_tc_prof[2 * base + 1] = (long long)(e & 0xffffffffffull);
+            }
         }
-        d_tc_prof_n = min(base + max(n, 0), d_tc_prof_cap);
+        d_tc_prof_n = base;
     }
 #endif
     if (warp == 0) tc::tmem_dealloc(sh->tmem_base, TC_TMEM_COLS);
 }
-__device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int warp, int lane) {
+__device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int lane) {
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform by construction
     t.tg = warp >> 3;
     t.smem = smem;
     t.act = smem + t.tg * (TC_NACT * TC_SLOT);
@@ -558,22 +751,72 @@ __device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcS
     t.rx = (uint32_t)(t.row & 7);
     t.half = (warp >> 2) & 1;
     t.trow = sh->tmem_base + t.tg * TC_TMEM_TILE + ((uint32_t)(32 * (warp & 3)) << 16);
-    t.acc_phase = 0; t.rec_phase = 0; t.cc = 0;
+    t.acc_phase = 0; t.rec_phase = 0; t.step_n = 0;
     t.pfree_bits = 0;
 }
-__device__ __forceinline__ void tc_load_step(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+__device__ __forceinline__ void tc_load_chunk(uint32_t src_off, uint32_t bytes, uint32_t& cc, unsigned char* smem, const unsigned char* wblob, int code) {
     TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
-    const TcTables* tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
-    unsigned char* ring = smem + TC_OFF_RING;
-    const TcStep S = tb->steps[st];
-#pragma unroll 1
-    for (int c = 0; c < S.nchunks; ++c, ++cc) {
-        const TcChunk ch = tb->chunks[S.chunk0 + c];
-        const uint32_t s = cc % TC_NRING;
-        tc::mbar_wait(&sh->wempty[s], ((cc / TC_NRING) & 1) ^ 1, sh->abort_flag, 300 + st);
-        tc::mbar_arrive_expect_tx(&sh->wfull[s], ch.bytes);
-        tc::bulk_g2s(ring + s * TC_SLOT, wblob + ch.src_off, ch.bytes, &sh->wfull[s]);
+    const uint32_t s = cc % TC_NRING;
+    tc::mbar_wait(&sh->wempty[s], ((cc / TC_NRING) & 1) ^ 1, sh->abort_flag, code);
+    tc::mbar_arrive_expect_tx(&sh->wfull[s], bytes);
+    tc::bulk_g2s(smem + TC_OFF_RING + s * TC_SLOT, wblob + src_off, bytes, &sh->wfull[s]);
+    ++cc;
+}
+// weight chunks of step ST (compile-time offsets and sizes)
+template <int ST, int C>
+__device__ __forceinline__ void tc_load_chunks(uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+    constexpr TcStep S = kProg.steps[ST];
+    if constexpr (C < S.nchunks) {
+        constexpr TcChunk ch = kProg.chunks[S.chunk0 + C];
+        tc_load_chunk(ch.src_off, ch.bytes, cc, smem, wblob, 300 + ST);
+        tc_load_chunks<ST, C + 1>(cc, smem, wblob);
     }
+}
+template <int ST>
+__device__ __forceinline__ void tc_load_step(uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+    tc_load_chunks<ST, 0>(cc, smem, wblob);
+}
+// table-driven variant (MMA self test)
+__device__ __forceinline__ void tc_load_step_dyn(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
+    const TcStep S = c_prog.steps[st];
+#pragma unroll 1
+    for (int c = 0; c < S.nchunks; ++c) {
+        const TcChunk ch = c_prog.chunks[S.chunk0 + c];
+        tc_load_chunk(ch.src_off, ch.bytes, cc, smem, wblob, 300 + st);
+    }
+}
+
+// MMA issuer warp of tile group TG (whole warp, converged).  TG is a template parameter and every counter derives from
+// kernel parameters and block indices, so that the compiler keeps the whole address arithmetic on the uniform datapath.
+template <int TG>
+__device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs) {
+    constexpr int tg = TG;
+    const uint32_t act_u32 = tc::smem_u32(tc_smem_raw) + TG * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(tc_smem_raw) + TC_OFF_RING;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, sh->tmem_base, 0) + TG * TC_TMEM_TILE;
+    const bool lead = tc_elect();
+    constexpr uint32_t cc_gm = kProg.cc_gm, cc_q = kProg.cc_q, cc_t = kProg.cc_t, cc_i = kProg.cc_i;
+    uint32_t n = 0, cc = 0;
+#define ISTEP(ST, COMMIT) tc_issuer_step<ST, COMMIT>(n, cc, sh, act_u32, ring_u32, tmem, tg, lead)
+#pragma unroll 1
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;
+#pragma unroll 1
+        for (int v = 0; v < V; ++v, cc += cc_gm) {
+            ISTEP(ST_G1, 0); ISTEP(ST_G3, 0); ISTEP(ST_G4, 0);
+            ISTEP(ST_M0, -1); ISTEP(ST_P0, 1); ISTEP(ST_P1, 2); ISTEP(ST_P2, 3); ISTEP(ST_P3, 1); ISTEP(ST_P4, 2); ISTEP(ST_P5, 0);
+            ISTEP(ST_M1, 0); ISTEP(ST_M2, 0); ISTEP(ST_M3, 0);
+        }
+        ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0); ISTEP(ST_Q3, 0);
+        cc += cc_q;
+#pragma unroll 1
+        for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
+#pragma unroll 1
+        for (int v = 0; v < V; ++v, cc += cc_i) {
+            ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
+            ISTEP(ST_I8, 0); ISTEP(ST_I9, 0);
+        }
+    }
+#undef ISTEP
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
@@ -591,35 +834,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     if (warp >= TC_TILES * 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
         // ===================================================== weight producer
-        if (warp == TC_TILES * 8 && lane == 0) {
+        if (warp == TC_TILES * 8 + 1) tc_issuer_warp<0>(sh, V, n_pairs);
+        else if (warp == TC_TILES * 8 + 2) tc_issuer_warp<1>(sh, V, n_pairs);
+        else if (warp == TC_TILES * 8 && lane == 0) {
             uint32_t cc = 0;
+#define LSTEP(ST) tc_load_step<ST>(cc, smem, A.wblob)
 #pragma unroll 1
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;        // a bounded wait gave up: drain
 #pragma unroll 1
-                for (int v = 0; v < V; ++v)
+                for (int v = 0; v < V; ++v) {       // attention layer 2 (ST_G2) runs in registers: no weights to stream
+                    LSTEP(ST_G1); LSTEP(ST_G3); LSTEP(ST_G4); LSTEP(ST_M0); LSTEP(ST_P0); LSTEP(ST_P1); LSTEP(ST_P2); LSTEP(ST_P3);
+                    LSTEP(ST_P4); LSTEP(ST_P5); LSTEP(ST_M1); LSTEP(ST_M2); LSTEP(ST_M3);
+                }
+                LSTEP(ST_Q1); LSTEP(ST_Q2); LSTEP(ST_Q3);
 #pragma unroll 1
-                    for (int st = ST_G1; st <= ST_M3; ++st)
-                        if (st != ST_G2) tc_load_step(st, cc, smem, A.wblob);       // attention layer 2 runs in registers
+                for (int v = 0; v < V; ++v) { LSTEP(ST_T1); LSTEP(ST_T2); LSTEP(ST_T3); LSTEP(ST_T4); }
 #pragma unroll 1
-                for (int st = ST_Q1; st <= ST_Q3; ++st) tc_load_step(st, cc, smem, A.wblob);
-#pragma unroll 1
-                for (int v = 0; v < V; ++v)
-#pragma unroll 1
-                    for (int st = ST_T1; st <= ST_T4; ++st) tc_load_step(st, cc, smem, A.wblob);
-#pragma unroll 1
-                for (int v = 0; v < V; ++v)
-#pragma unroll 1
-                    for (int st = ST_I1; st <= ST_I9; ++st) tc_load_step(st, cc, smem, A.wblob);
+                for (int v = 0; v < V; ++v) {
+                    LSTEP(ST_I1); LSTEP(ST_I2); LSTEP(ST_I3); LSTEP(ST_I4); LSTEP(ST_I5); LSTEP(ST_I6); LSTEP(ST_I7); LSTEP(ST_I8); LSTEP(ST_I9);
+                }
             }
+#undef LSTEP
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
         // ===================================================== tile threads
         TcTile t;
-        tc_tile_init(t, smem, sh, warp, lane);
+        tc_tile_init(t, smem, sh, lane);
         const int row = t.row, h = t.half, tg = t.tg;
-        const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's MMAs and record loads
+        const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
 
 #pragma unroll 1
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
@@ -1076,11 +1320,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_selftest(const TcTables* t
     if (warp == TC_TILES * 8) {
         if (lane == 0) {
             uint32_t cc = 0;
-            tc_load_step(0, cc, smem, wblob);
+            tc_load_step_dyn(0, cc, smem, wblob);
         }
+    } else if (warp == TC_TILES * 8 + 1) {       // MMA issuer of tile group 0: one step
+        const uint32_t tmem = __shfl_sync(0xffffffffu, sh->tmem_base, 0);
+        tc::mbar_wait(&sh->ready[0][0], 0, sh->abort_flag, 600);
+        tc::tcgen05_fence_after();
+        tc_issue_ops_dyn(0, 0, sh, tc::smem_u32(tc_smem_raw), tc::smem_u32(tc_smem_raw) + TC_OFF_RING, tmem, 0);
     } else if (warp < 8) {
         TcTile t;
-        tc_tile_init(t, smem, sh, warp, lane);
+        tc_tile_init(t, smem, sh, lane);
         // operand: columns [64 s, 64 s + 64) of A -> slot s; this thread converts chunks 4 h .. 4 h + 3 of its row
         for (int s = 0; s * 64 < K; ++s)
             for (int c = 4 * t.half; c < 4 * t.half + 4; ++c) {
@@ -1103,7 +1352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_selftest(const TcTables* t
 }
 
 // One-step table for the self test: K columns over slots 0.., identity K order.
-static void tc_build_single(const float* W, int N, int K, TcTables& T, std::vector<uint16_t>& blob) {
+static void tc_build_single(const float* W, int N, int K, TcProg& T, std::vector<uint16_t>& blob) {
     memset(&T, 0, sizeof(T));
     blob.clear();
     const int n_pad = (N + 15) & ~15;
@@ -1140,4 +1389,53 @@ static void tc_build_single(const float* W, int N, int K, TcTables& T, std::vect
     }
     T.ops[n_ops - 1].last_in_chunk = 1;
     T.steps[0].op0 = 0; T.steps[0].nops = (uint16_t)n_ops; T.steps[0].chunk0 = 0; T.steps[0].nchunks = (uint16_t)n_chunks;
+}
+
+// ================================================================================================ MMA pacing probe
+// Developer measurement (vanerf_tc_mma_probe): one warp issues `reps` tcgen05.mma (M = 128, N = n, K = 16, operands =
+// whatever the shared memory holds) round-robin over `n_acc` accumulators and reports, per CTA, the cycles spent
+// issuing and the cycles until the last MMA has completed.  mode bit 0: a second warp issues the same stream into the
+// other TMEM half concurrently (two tiles per SM).
+__global__ void __launch_bounds__(128, 1) k_tc_mma_probe(int n, int reps, int n_acc, int mode, long long* out) {
+    unsigned char* smem = tc_smem_raw;
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_slot;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    for (int i = threadIdx.x; i < (6 * TC_SLOT) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { tc::mbar_init(&bar[0], 1); tc::mbar_init(&bar[1], 1); tc::mbar_fence_init(); }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    tc::fence_proxy_async();
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    tc::tcgen05_fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    if (warp < 2 && (warp == 0 || (mode & 1))) {
+        const uint32_t base = tc::smem_u32(smem) + warp * 2 * TC_SLOT;
+        const uint32_t idesc = tc::umma_idesc_bf16(128, n);
+        const bool lead = tc_elect();
+        const long long t0 = clock64();
+        const uint32_t a0 = tmem + warp * 256, a1 = a0 + (uint32_t)(1 % n_acc) * n, a2 = a0 + (uint32_t)(2 % n_acc) * n, a3 = a0 + (uint32_t)(3 % n_acc) * n;
+        const uint64_t ad = tc_desc(base), bd = tc_desc(base + TC_SLOT);
+        if (lead) {
+#pragma unroll 1
+            for (int r = 0; r < reps; r += 4) {          // four K steps of one 64-column operand slot per iteration
+                tc::umma_bf16(a0, ad, bd, idesc, 1u);
+                tc::umma_bf16(a1, ad + 2, bd + 2, idesc, 1u);
+                tc::umma_bf16(a2, ad + 4, bd + 4, idesc, 1u);
+                tc::umma_bf16(a3, ad + 6, bd + 6, idesc, 1u);
+            }
+            tc::umma_commit(&bar[warp]);
+        }
+        __syncwarp();
+        const long long t1 = clock64();
+        while (!tc::mbar_try_wait(&bar[warp], 0)) {}
+        const long long t2 = clock64();
+        if (lead) {
+            out[(blockIdx.x * 2 + warp) * 2] = t1 - t0;
+            out[(blockIdx.x * 2 + warp) * 2 + 1] = t2 - t0;
+        }
+    }
+    tc::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }

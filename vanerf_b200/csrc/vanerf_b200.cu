@@ -43,7 +43,8 @@ struct vanerf_ctx {
     DevBuf wblob, netdev;
 #ifndef VANERF_HOST_EMUL
     // tensor-core path: step tables + bf16 weight images, bf16 maps / vertex tables, operand images, error flag
-    TcTables h_tc;                     // host copy of the step tables / biases (weights) + camera-space keypoints (frame)
+    TcTables h_tc;                     // host copy of the biases / small fp32 layers (weights) + camera-space keypoints (frame)
+    TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
     DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
     FrameTc ft;
@@ -115,6 +116,7 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     memset(c->tc_err_host, 0, 8 * sizeof(int));
     memset(&c->ft, 0, sizeof(c->ft));
     memset(&c->h_tc, 0, sizeof(c->h_tc));
+    memset(&c->h_prog, 0, sizeof(c->h_prog));
 #endif
     *out = c;
     return VANERF_OK;
@@ -199,7 +201,7 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
         std::vector<uint16_t> img;
         float kpt_keep[TC_MAXV * NKPT * 4];
         memcpy(kpt_keep, ctx->h_tc.kpt4, sizeof(kpt_keep));
-        tc_build(src, w->ani_al, ctx->h_tc, img);
+        tc_build(src, w->ani_al, ctx->h_tc, ctx->h_prog, img);
         memcpy(ctx->h_tc.kpt4, kpt_keep, sizeof(kpt_keep));
         ctx->tc_tab_dirty = true;
         ENSURE(ctx, ctx->tcw, img.size() * 2);
@@ -375,6 +377,10 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_set = true;
     }
+    if (!tc_program_matches(ctx->h_prog)) {           // the kernels execute the compile-time copy (kProg)
+        snprintf(ctx->err, sizeof(ctx->err), "tensor-core path: packing script and compiled MMA program disagree");
+        return VANERF_ERR_STATE;
+    }
     if (ctx->tc_tab_dirty) {            // stream-ordered: earlier launches on this stream have read the old tables
         ENSURE(ctx, ctx->tctab, sizeof(TcTables));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tctab.p, &ctx->h_tc, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
@@ -506,14 +512,16 @@ int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host,
 #ifndef VANERF_HOST_EMUL
     if (!ctx || !A_dev || !W_host || !D_dev || K <= 0 || K > 256 || (K & 15) || N <= 0 || N > 128) return ctx_invalid(ctx, "vanerf_tc_selftest");
     cudaStream_t stream = (cudaStream_t)stream_;
-    static TcTables T;
+    static TcProg P;
+    static TcTables T;                 // biases etc. are not used by the self test
     std::vector<uint16_t> img;
-    tc_build_single(W_host, N, K, T, img);
+    tc_build_single(W_host, N, K, P, img);
     DevBuf blob, tab;
     ENSURE(ctx, blob, img.size() * 2);
     ENSURE(ctx, tab, sizeof(TcTables));
     CUDA_TRY(ctx, cudaMemcpyAsync(tab.p, &T, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(blob.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(TcProg), 0, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     VANERF_LAUNCH(k_tc_selftest, 1, TC_THREADS, TC_SMEM_BYTES, stream, (const TcTables*)tab.p, (const unsigned char*)blob.p, A_dev, K,
                   (N + 15) & ~15, D_dev, ctx->tc_err_dev);
@@ -528,6 +536,54 @@ int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host,
     return VANERF_OK;
 #else
     (void)A_dev; (void)W_host; (void)K; (void)N; (void)D_dev; (void)stream_;
+    return ctx_invalid(ctx, "tensor-core path needs the CUDA build");
+#endif
+}
+
+// 0 when the weight-packing script (run here with zero weights, no GPU needed) yields exactly the MMA program the
+// tensor-core kernels were compiled with.
+int vanerf_tc_program_check(void) {
+#ifndef VANERF_HOST_EMUL
+    static const int dims[L_COUNT][2] = {
+        {10, 196}, {3, 10}, {64, 196}, {64, 64}, {10, 28}, {3, 10}, {8, 28}, {8, 8},
+        {128, 358}, {128, 128}, {120, 136}, {64, 120}, {64, 128}, {64, 64}, {2, 64}, {24, 128},
+        {96, 96}, {6, 96}, {96, 96}, {40, 96},
+        {16, 4}, {40, 16}, {64, 120}, {32, 64}, {32, 32}, {33, 32}, {32, 32}, {1, 32}, {16, 37}, {8, 16}, {1, 8}};
+    std::vector<std::vector<float>> w(L_COUNT);
+    std::vector<vanerf_linear> lin(L_COUNT);
+    const vanerf_linear* src[L_COUNT];
+    for (int i = 0; i < L_COUNT; ++i) {
+        w[i].assign((size_t)dims[i][0] * dims[i][1], 0.0f);
+        lin[i].w = w[i].data(); lin[i].b = nullptr; lin[i].out_dim = dims[i][0]; lin[i].in_dim = dims[i][1];
+        src[i] = &lin[i];
+    }
+    static TcTables T;
+    static TcProg P;
+    std::vector<uint16_t> img;
+    tc_build(src, 0.0f, T, P, img);
+    return tc_program_matches(P) ? 0 : 1;
+#else
+    return 0;
+#endif
+}
+
+// Developer measurement: pacing of small tcgen05.mma (see k_tc_mma_probe).  out_host: (2 warps, 2) cycles of CTA 0
+// [issue, issue + completion]; n_ctas CTAs run the same stream concurrently.
+int vanerf_tc_mma_probe(vanerf_ctx* ctx, int32_t n, int32_t reps, int32_t n_acc, int32_t mode, int32_t n_ctas, long long* out_host) {
+#ifndef VANERF_HOST_EMUL
+    if (!ctx || !out_host || n < 16 || n > 256 || (n & 15) || reps <= 0 || n_acc <= 0 || n_acc * n > 256 || n_ctas <= 0) return ctx_invalid(ctx, "vanerf_tc_mma_probe");
+    long long* d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, (size_t)n_ctas * 4 * sizeof(long long)));
+    CUDA_TRY(ctx, cudaMemset(d, 0, (size_t)n_ctas * 4 * sizeof(long long)));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TC_SLOT + 1024));
+    k_tc_mma_probe<<<n_ctas, 128, 6 * TC_SLOT + 1024>>>(n, reps, n_acc, mode, d);
+    CHECK_LAUNCH(ctx);
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    CUDA_TRY(ctx, cudaMemcpy(out_host, d, 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return VANERF_OK;
+#else
+    (void)n; (void)reps; (void)n_acc; (void)mode; (void)n_ctas; (void)out_host;
     return ctx_invalid(ctx, "tensor-core path needs the CUDA build");
 #endif
 }
