@@ -75,7 +75,11 @@ def test_cuda_full_view_properties(cuda_lib):
     oc, of = r.render_rays(tar, pix, 64, 64, True)
     oc, of = oc.cpu().numpy(), of.cpu().numpy()
     assert np.isfinite(oc).all() and np.isfinite(of).all()
-    assert np.abs(oc[:, 4] - 1).max() < 1e-4 and np.abs(of[:, 4] - 1).max() < 1e-4, "alpha == 1 (last interval is 1e10, B-7)"
+    # the last interval is 1e10 (B-7), so alpha saturates at 1 wherever the last sample's density has not underflowed;
+    # rays that stay ~0.5 m away from the hands end at 1 - exp(-sigmoid(-sdf/beta)/beta * 1e10) ~ 0.993 (oracle: same)
+    for a in (oc[:, 4], of[:, 4]):
+        assert a.max() < 1 + 1e-4 and a.min() > 0.95, "alpha in (0.95, 1]"
+        assert (np.abs(a - 1) < 1e-4).mean() > 0.2, "alpha == 1 on the rays that come close to the hands"
     assert (of[:, 3] > 0.5).all() and (of[:, 3] < 1.6).all(), "depth inside the frustum"
     # the chunked full-view call must equal the same rays rendered as a small batch (chunk-boundary independence)
     sel = np.random.RandomState(0).choice(R, 96, replace=False)

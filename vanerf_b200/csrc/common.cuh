@@ -98,6 +98,11 @@ struct FrameDev {                 // filled by vanerf_frame_setup, passed by val
     const int* faces;                      // (F,3)
     const float4* tri_nodes; const int* tri_prims;   // BVH over triangles (prims = face ids in leaf order)
     const float4* vtx_nodes; const int* vtx_prims;   // BVH over vertices
+    // per-primitive records in leaf order, so that a leaf visit is one dependent load instead of prims -> faces -> verts:
+    // triangle = 4 x float4 {a.xyz, as_float(face id)}, {b.xyz, ab.x}, {c.xyz, ab.y}, {ab.z, ac.xyz} with ab = b - a,
+    // ac = c - a rounded exactly as the kernels' xsub does; vertex = {xyz, as_float(vertex id)}
+    const float4* tri_rec;
+    const float4* vtx_rec;
 };
 
 struct TargetDev {

@@ -98,19 +98,39 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             ray = rays + (size_t)(n / S) * VANERF_RAY_STRIDE;
             sample_point(ray, tar.cam_pos, z[n], p);
         }
-        ViewProj pr[MAXV];
+        // ---- pass 1, one lane per view (lane v < V of the sample's 8 lanes; the same exact-op sequence as before,
+        // just not repeated by all 8 lanes): projection, in-frustum and foreground masks, boundary weight, and the
+        // bilinear tap set of the 64-channel map; the results are shared with 8-wide shuffles.
+        float mx = 0.f, my = 0.f, mw = 0.f;
+        int mok = 1;
+        Bilin mb;
+        mb.i00 = mb.i01 = mb.i10 = mb.i11 = 0; mb.nw = mb.ne = mb.sw = mb.se = 0.f;
+        if (lane < V) {
+            const int v = lane;
+            const ViewProj q = project_sample(fr, v, p);
+            const Bilin b = bilin_setup(q.x, q.y, fr.W, fr.H);
+            const float* mp = fr.imgm + (size_t)v * fr.H * fr.W * 4 + 3;
+            const float fgv = bilin_mix(b, mp[(size_t)b.i00 * 4], b.i01 >= 0 ? mp[(size_t)b.i01 * 4] : 0.f,
+                                        b.i10 >= 0 ? mp[(size_t)b.i10 * 4] : 0.f, b.i11 >= 0 ? mp[(size_t)b.i11 * 4] : 0.f);
+            mok = (q.in && fgv > 0.1f) ? 1 : 0;
+            float w = 1.0f;
+            const float q3[3] = {q.x, q.y, q.zn};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float qq = 0.5f * q3[c] + 0.5f;
+                const float d = fminf(qq, 1.0f - qq);
+                w *= sigmoidf_(5.0f * (d / 0.1f - 1.0f));
+            }
+            mx = q.x; my = q.y; mw = w;
+            mb = bilin_setup(q.x, q.y, fr.g0w, fr.g0h);
+        }
         float pw[MAXV];
         bool m = true;
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
             if (v < V) {
-                pr[v] = project_sample(fr, v, p);
-                const Bilin b = bilin_setup(pr[v].x, pr[v].y, fr.W, fr.H);
-                const float* mp = fr.imgm + (size_t)v * fr.H * fr.W * 4 + 3;
-                const float fgv = bilin_mix(b, mp[(size_t)b.i00 * 4], b.i01 >= 0 ? mp[(size_t)b.i01 * 4] : 0.f,
-                                            b.i10 >= 0 ? mp[(size_t)b.i10 * 4] : 0.f, b.i11 >= 0 ? mp[(size_t)b.i11 * 4] : 0.f);
-                pr[v].fg = fgv > 0.1f;
-                m = m && pr[v].in && pr[v].fg;
+                pw[v] = __shfl_sync(0xffffffffu, mw, v, 8);
+                m = m && (__shfl_sync(0xffffffffu, mok, v, 8) != 0);
             }
         }
         const float mf = m ? 1.0f : 0.0f;
@@ -118,15 +138,7 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
             if (v < V) {
-                float w = 1.0f;
-                const float q3[3] = {pr[v].x, pr[v].y, pr[v].zn};
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float q = 0.5f * q3[c] + 0.5f;
-                    const float d = fminf(q, 1.0f - q);
-                    w *= sigmoidf_(5.0f * (d / 0.1f - 1.0f));
-                }
-                pw[v] = w * mf;
+                pw[v] = pw[v] * mf;
                 pw_sum += pw[v];
             }
         }
@@ -140,14 +152,16 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
         for (int v = 0; v < MAXV; ++v) {
             if (v >= V) break;
             unsigned char* img = rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
-            const float x = pr[v].x, y = pr[v].y;
+            const float x = __shfl_sync(0xffffffffu, mx, v, 8), y = __shfl_sync(0xffffffffu, my, v, 8);
+            Bilin b64;
+            b64.i00 = __shfl_sync(0xffffffffu, mb.i00, v, 8); b64.i01 = __shfl_sync(0xffffffffu, mb.i01, v, 8);
+            b64.i10 = __shfl_sync(0xffffffffu, mb.i10, v, 8); b64.i11 = __shfl_sync(0xffffffffu, mb.i11, v, 8);
+            b64.nw = __shfl_sync(0xffffffffu, mb.nw, v, 8); b64.ne = __shfl_sync(0xffffffffu, mb.ne, v, 8);
+            b64.sw = __shfl_sync(0xffffffffu, mb.sw, v, 8); b64.se = __shfl_sync(0xffffffffu, mb.se, v, 8);
             const size_t vb = (size_t)v * fr.n_verts;
             const float qv = qvis[(size_t)v * N_total + n] ? 1.0f : 0.0f, vn = fr.vis[vb + nn], vt = fr.vis[vb + tw];
             // R0: pixel-aligned geo0, R1 / R2: nearest / twin vertex rows (already multiplied by visibility)
-            {
-                const Bilin b = bilin_setup(x, y, fr.g0w, fr.g0h);
-                *reinterpret_cast<uint4*>(img + off) = tap8_bf16(ft.geo0 + (size_t)v * fr.g0h * fr.g0w * 64, 64, 8 * lane, b);
-            }
+            *reinterpret_cast<uint4*>(img + off) = tap8_bf16(ft.geo0 + (size_t)v * fr.g0h * fr.g0w * 64, 64, 8 * lane, b64);
             *reinterpret_cast<uint4*>(img + TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + nn) * 64 + 8 * lane);
             *reinterpret_cast<uint4*>(img + 2 * TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + tw) * 64 + 8 * lane);
             // R3 (misc): c0 [sdf,qvis,vn,vt,0..] | c1 0 | c2 px8 | c3 a8 | c4 b8 | c5 [sdf,qvis,vn,vt,0..] | c6,c7 0

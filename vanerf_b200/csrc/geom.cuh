@@ -9,9 +9,9 @@
 
 #define BVH_STACK 48
 
-__device__ __forceinline__ float point_tri_dist2(const float* p, const float* a, const float* b, const float* c) {
-    const float ab0 = xsub(b[0], a[0]), ab1 = xsub(b[1], a[1]), ab2 = xsub(b[2], a[2]);
-    const float ac0 = xsub(c[0], a[0]), ac1 = xsub(c[1], a[1]), ac2 = xsub(c[2], a[2]);
+// ab = b - a and ac = c - a are passed in (precomputed per frame with the same rounding as xsub)
+__device__ __forceinline__ float point_tri_dist2(const float* p, const float* a, const float* b, const float* c,
+                                                 float ab0, float ab1, float ab2, float ac0, float ac1, float ac2) {
     const float ap0 = xsub(p[0], a[0]), ap1 = xsub(p[1], a[1]), ap2 = xsub(p[2], a[2]);
     float q0, q1, q2;
     const float d1 = xdot3(ab0, ab1, ab2, ap0, ap1, ap2), d2 = xdot3(ac0, ac1, ac2, ap0, ap1, ap2);
@@ -91,9 +91,11 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
-                const int f = fr.tri_prims[first + i];
-                const int* fv = fr.faces + 3 * f;
-                const float d = point_tri_dist2(p, fr.verts + 3 * fv[0], fr.verts + 3 * fv[1], fr.verts + 3 * fv[2]);
+                const float4* rec = fr.tri_rec + 4 * (first + i);
+                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+                const int f = __float_as_int(r0.w);
+                const float va[3] = {r0.x, r0.y, r0.z}, vb[3] = {r1.x, r1.y, r1.z}, vc[3] = {r2.x, r2.y, r2.z};
+                const float d = point_tri_dist2(p, va, vb, vc, r1.w, r2.w, r3.x, r3.y, r3.z, r3.w);
                 if (d < best_d || (d == best_d && f < best_f)) { best_d = d; best_f = f; }
             }
         } else {
@@ -121,13 +123,11 @@ __device__ __forceinline__ bool inside_parity(const FrameDev& fr, const float* p
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
-                const int f = fr.tri_prims[first + i];
-                const int* fv = fr.faces + 3 * f;
-                const float* v0 = fr.verts + 3 * fv[0];
-                const float* v1 = fr.verts + 3 * fv[1];
-                const float* v2 = fr.verts + 3 * fv[2];
-                const float e10 = xsub(v1[0], v0[0]), e11 = xsub(v1[1], v0[1]), e12 = xsub(v1[2], v0[2]);
-                const float e20 = xsub(v2[0], v0[0]), e21 = xsub(v2[1], v0[1]), e22 = xsub(v2[2], v0[2]);
+                const float4* rec = fr.tri_rec + 4 * (first + i);
+                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+                const float v0[3] = {r0.x, r0.y, r0.z};
+                const float e10 = r1.w, e11 = r2.w, e12 = r3.x;        // v1 - v0
+                const float e20 = r3.y, e21 = r3.z, e22 = r3.w;        // v2 - v0
                 const float aa = xsub(xmul(e12, e21), xmul(e11, e22));
                 if (fabsf(aa) < 1e-20f) continue;
                 const float inv = xdiv(1.0f, aa);
@@ -164,8 +164,9 @@ __device__ __forceinline__ int nearest_vertex(const FrameDev& fr, const float* p
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
-                const int j = fr.vtx_prims[first + i];
-                const float dx = xsub(p[0], fr.verts[3 * j]), dy = xsub(p[1], fr.verts[3 * j + 1]), dz = xsub(p[2], fr.verts[3 * j + 2]);
+                const float4 vr = fr.vtx_rec[first + i];
+                const int j = __float_as_int(vr.w);
+                const float dx = xsub(p[0], vr.x), dy = xsub(p[1], vr.y), dz = xsub(p[2], vr.z);
                 const float d = xadd(xadd(xmul(dx, dx), xmul(dy, dy)), xmul(dz, dz));
                 if (d < best_d || (d == best_d && j < best_i)) { best_d = d; best_i = j; }
             }

@@ -630,16 +630,20 @@ struct TcTile {
         TC_PROF(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
-    // multiply the 8 bf16 of a chunk by one gate (packed bf16 multiply; g2 = the gate in both halves)
-    __device__ __forceinline__ void gate_chunk1(int s, int chunk, uint32_t g2) const {
-        uint4 q = ld_chunk(s, chunk);
-        q.x = tc_mul2(q.x, g2); q.y = tc_mul2(q.y, g2); q.z = tc_mul2(q.z, g2); q.w = tc_mul2(q.w, g2);
-        st_chunk(s, chunk, q);
+    // multiply the 8 bf16 of a chunk by per-element gates (fp32 product, one rounding back to bf16)
+    __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
+        float f[8];
+        unpack8(ld_chunk(s, chunk), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= g[i];
+        st_chunk(s, chunk, pack8(f));
     }
-    __device__ __forceinline__ void gate_chunk4(int s, int chunk, uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3) const {
-        uint4 q = ld_chunk(s, chunk);
-        q.x = tc_mul2(q.x, g0); q.y = tc_mul2(q.y, g1); q.z = tc_mul2(q.z, g2); q.w = tc_mul2(q.w, g3);
-        st_chunk(s, chunk, q);
+    __device__ __forceinline__ void gate_chunk1(int s, int chunk, float g) const {
+        float f[8];
+        unpack8(ld_chunk(s, chunk), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= g;
+        st_chunk(s, chunk, pack8(f));
     }
 };
 
@@ -914,13 +918,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         g8[j] = tc_act<TA_SIGMOID>(s);
                     }
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const uint32_t g2 = tc_dup_bf16(g64[s]);
+                    for (int s = 0; s < 3; ++s)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g2);
-                    }
-                    if (h == 0) t.gate_chunk1(3, 2, tc_dup_bf16(g8[0]));
-                    else { t.gate_chunk1(3, 3, tc_dup_bf16(g8[1])); t.gate_chunk1(3, 4, tc_dup_bf16(g8[2])); }
+                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g64[s]);
+                    if (h == 0) t.gate_chunk1(3, 2, g8[0]);
+                    else { t.gate_chunk1(3, 3, g8[1]); t.gate_chunk1(3, 4, g8[2]); }
                 }
                 // ---- G3: fused layer 1 (ReLU)
                 t.step(ST_G3);
@@ -1075,19 +1077,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 {
                     float gt[8];
                     t.ld8(0, gt);
-                    uint32_t g2[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { gt[i] = tc_act<TA_SIGMOID>(gt[i]); g2[i] = tc_dup_bf16(gt[i]); }
+                    for (int i = 0; i < 6; ++i) gt[i] = tc_act<TA_SIGMOID>(gt[i]);
                     // slot 1 chunks: 0 -> g0, 1 -> g1, 2 -> g2, 3,4 -> g3, 5,6 -> g4, 7 -> [g3,g3,g4,g4,g0,g0,g0,g1]
                     // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (kTexMap1 / kTexMap2)
                     if (h == 0) {
-                        t.gate_chunk1(1, 0, g2[0]); t.gate_chunk1(1, 1, g2[1]); t.gate_chunk1(1, 2, g2[2]); t.gate_chunk1(1, 3, g2[3]);
-                        t.gate_chunk1(2, 0, g2[5]); t.gate_chunk1(2, 1, g2[5]);
+                        t.gate_chunk1(1, 0, gt[0]); t.gate_chunk1(1, 1, gt[1]); t.gate_chunk1(1, 2, gt[2]); t.gate_chunk1(1, 3, gt[3]);
+                        t.gate_chunk1(2, 0, gt[5]); t.gate_chunk1(2, 1, gt[5]);
                     } else {
-                        t.gate_chunk1(1, 4, g2[3]); t.gate_chunk1(1, 5, g2[4]); t.gate_chunk1(1, 6, g2[4]);
-                        t.gate_chunk4(1, 7, g2[3], g2[4], g2[0], tc::pack_bf16(gt[0], gt[1]));
-                        t.gate_chunk1(2, 2, g2[5]);
-                        t.gate_chunk4(2, 3, g2[1], g2[2], tc::pack_bf16(gt[2], 1.0f), 0x3F803F80u);
+                        t.gate_chunk1(1, 4, gt[3]); t.gate_chunk1(1, 5, gt[4]); t.gate_chunk1(1, 6, gt[4]);
+                        const float g7[8] = {gt[3], gt[3], gt[4], gt[4], gt[0], gt[0], gt[0], gt[1]};
+                        t.gate_chunk(1, 7, g7);
+                        t.gate_chunk1(2, 2, gt[5]);
+                        const float g3[8] = {gt[1], gt[1], gt[2], gt[2], gt[2], 1.0f, 1.0f, 1.0f};
+                        t.gate_chunk(2, 3, g3);
                     }
                     const int fcol = TC_SREG + 40 * v;
                     if (h == 0) {

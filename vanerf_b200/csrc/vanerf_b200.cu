@@ -57,7 +57,7 @@ struct vanerf_ctx {
     FrameDev fr;
     bool have_frame = false;
     DevBuf geo0, geo1, tex, imgm, T64, T8, Ttex, vis, verts, faces, tri_nodes, tri_prims, vtx_nodes, vtx_prims,
-        kpt_cam, xyz_ndc, xy11, zbuf;
+        kpt_cam, xyz_ndc, xy11, zbuf, tri_rec, vtx_rec;
     // scratch
     DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
 };
@@ -131,7 +131,7 @@ void vanerf_ctx_destroy(vanerf_ctx* c) {
 #endif
     DevBuf* all[] = {&c->wblob, &c->netdev, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
                      &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
-                     &c->xyz_ndc, &c->xy11, &c->zbuf, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
+                     &c->xyz_ndc, &c->xy11, &c->zbuf, &c->tri_rec, &c->vtx_rec, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
                      &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     delete c;
@@ -247,6 +247,27 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     bvh::build_triangles(f->verts, f->faces, F, tt);
     bvh::build_points(f->verts, Nv, vt);
 
+    // per-primitive records in leaf order (see FrameDev); b - a and c - a are rounded once, exactly like xsub
+    std::vector<float> trec((size_t)tt.prims.size() * 16), vrec((size_t)vt.prims.size() * 4);
+    for (size_t i = 0; i < tt.prims.size(); ++i) {
+        const int fi = tt.prims[i];
+        const float* a = f->verts + 3 * f->faces[3 * fi];
+        const float* b = f->verts + 3 * f->faces[3 * fi + 1];
+        const float* c = f->verts + 3 * f->faces[3 * fi + 2];
+        volatile float ab[3], ac[3];
+        for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
+        float* r = &trec[16 * i];
+        r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = bvh::as_float(fi);
+        r[4] = b[0]; r[5] = b[1]; r[6] = b[2]; r[7] = ab[0];
+        r[8] = c[0]; r[9] = c[1]; r[10] = c[2]; r[11] = ab[1];
+        r[12] = ab[2]; r[13] = ac[0]; r[14] = ac[1]; r[15] = ac[2];
+    }
+    for (size_t i = 0; i < vt.prims.size(); ++i) {
+        const int vi = vt.prims[i];
+        float* r = &vrec[4 * i];
+        r[0] = f->verts[3 * vi]; r[1] = f->verts[3 * vi + 1]; r[2] = f->verts[3 * vi + 2]; r[3] = bvh::as_float(vi);
+    }
+
     const size_t g0n = (size_t)V * 64 * fr.g0h * fr.g0w, g1n = (size_t)V * 8 * fr.g1h * fr.g1w, txn = (size_t)V * 8 * fr.th * fr.tw;
     ENSURE(ctx, ctx->geo0, g0n * 4); ENSURE(ctx, ctx->geo1, g1n * 4); ENSURE(ctx, ctx->tex, txn * 4);
     ENSURE(ctx, ctx->imgm, (size_t)V * H * W * 16);
@@ -256,6 +277,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     ENSURE(ctx, ctx->tri_nodes, tt.nodes.size() * 4); ENSURE(ctx, ctx->tri_prims, tt.prims.size() * 4);
     ENSURE(ctx, ctx->vtx_nodes, vt.nodes.size() * 4); ENSURE(ctx, ctx->vtx_prims, vt.prims.size() * 4);
     ENSURE(ctx, ctx->kpt_cam, kc.size() * 4);
+    ENSURE(ctx, ctx->tri_rec, trec.size() * 4); ENSURE(ctx, ctx->vtx_rec, vrec.size() * 4);
     ENSURE(ctx, ctx->xyz_ndc, (size_t)V * Nv * 12); ENSURE(ctx, ctx->xy11, (size_t)V * Nv * 8);
     ENSURE(ctx, ctx->zbuf, (size_t)V * RASTER_S * RASTER_S * 8);
 
@@ -266,6 +288,8 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_nodes.p, vt.nodes.data(), vt.nodes.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_prims.p, vt.prims.data(), vt.prims.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kpt_cam.p, kc.data(), kc.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_rec.p, trec.data(), trec.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_rec.p, vrec.data(), vrec.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(stream));       // pageable host staging above goes out of scope
 
     fr.geo0 = (const float*)ctx->geo0.p; fr.geo1 = (const float*)ctx->geo1.p; fr.tex = (const float*)ctx->tex.p;
@@ -276,6 +300,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     fr.tri_nodes = (const float4*)ctx->tri_nodes.p; fr.tri_prims = (const int*)ctx->tri_prims.p;
     fr.vtx_nodes = (const float4*)ctx->vtx_nodes.p; fr.vtx_prims = (const int*)ctx->vtx_prims.p;
     fr.kpt_cam = (const float*)ctx->kpt_cam.p;
+    fr.tri_rec = (const float4*)ctx->tri_rec.p; fr.vtx_rec = (const float4*)ctx->vtx_rec.p;
 
     const int T = 256;
     TimedScope ts(ctx, KCL_SETUP, stream);
