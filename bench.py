@@ -78,6 +78,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture
+    (profiles/r01_<precision>_traffic.json, written by tools/ncu_key.py); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", f"r01_{precision}_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def partition(rank, world):
     """Interleaved pixel partition: G=2 -> 1x2, 4 -> 2x2, 8 -> 4x2 (y-period x x-period)."""
     gy, gx = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
@@ -138,7 +148,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("VANERF_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    # headline = the bf16-MLP tensor-core path (north star kernel 2); the fp32 FFMA path is measured next to it
+    ap.add_argument("--precision", default=os.environ.get("VANERF_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-fp32-path", action="store_true", help="skip the secondary fp32-path measurement")
     ap.add_argument("--workload", default="B", choices=["B", "C"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -259,6 +271,20 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = H * W / float(te.item())
 
+    # ---------------- the other precision path of BASELINE.json configs[1], one timed view (N = 1 only)
+    fp32_extra = None
+    if world == 1 and args.precision == "bf16" and not args.no_fp32_path:
+        r.render_rays(tar, pix, S_C, S_F, True, L.FP32)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1)
+        a.record()
+        r.render_rays(tar, pix, S_C, S_F, True, L.FP32)
+        b.record()
+        torch.cuda.synchronize()
+        fp32_extra = {"ms_per_view": a.elapsed_time(b), "value": H * W / (a.elapsed_time(b) * 1e-3), "unit": "rays/s",
+                      "note": "fp32 FFMA path (k_gather + k_mlp_simt), 1 warm-up + 1 timed view, inputs resident"}
+
     if rank == 0:
         pk = peaks()
         clk = clocks.stop()
@@ -267,7 +293,8 @@ def main():
         gat_ms, gat_n = ktimes["gather"]
         flops = FLOP_PER_SAMPLE(V) * n_samples_step * args.steps
         ach_tf = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        gbytes = GATHER_BYTES_PER_SAMPLE(V, 4) * n_samples_step * args.steps
+        gather_elem = 4 if args.precision == "fp32" else 2          # fp32 maps vs bf16 maps / vertex tables
+        gbytes = GATHER_BYTES_PER_SAMPLE(V, gather_elem) * n_samples_step * args.steps
         ach_gb = gbytes / (gat_ms * 1e-3) / 1e9 if gat_ms > 0 else 0.0
         line = {
             "metric": "rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": W_steps,
@@ -278,15 +305,18 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_mlp_simt (fused PE + fusion + MLP, fp32 FFMA)" if args.precision == "fp32" else "k_mlp_tc (tcgen05)",
                          "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": ach_tf / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                         "frac": ach_tf / pk["tf_sust"], "traffic": ncu_traffic(args.precision),
+                         "peak_source": pk["src"] + " bf16 sustained",
                          "launches": int(mlp_n), "avg_launch_ms": mlp_ms / max(1, mlp_n),
                          "algorithmic_flop_per_sample": FLOP_PER_SAMPLE(V)},
-            "roofline_gather": {"kernel": "k_gather", "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"], "unit": "GB/s",
+            "roofline_gather": {"kernel": "k_gather" if args.precision == "fp32" else "k_gather_tc", "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"], "unit": "GB/s",
                                 "frac": ach_gb / pk["hbm"], "launches": int(gat_n), "avg_launch_ms": gat_ms / max(1, gat_n),
-                                "algorithmic_bytes_per_sample": GATHER_BYTES_PER_SAMPLE(V, 4)},
+                                "algorithmic_bytes_per_sample": GATHER_BYTES_PER_SAMPLE(V, gather_elem)},
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
             "clocks": clk,
         }
+        if fp32_extra is not None:
+            line["fp32_path"] = fp32_extra
         if world == 1 and not args.no_cpu_baseline:
             rps, sec, n = cpu_port_rays_per_s(32, False)
             line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
