@@ -163,6 +163,8 @@ def main():
     from vanerf_b200 import synthetic, weights
     from vanerf_b200.model import VANeRF
 
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
