@@ -63,7 +63,7 @@ struct TcOp {
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
 struct TcChunk { uint32_t src_off, bytes; };
-#define TC_MAX_OPS 64
+#define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
 #define TC_MAX_BIAS 1024
 struct TcTables {                        // global memory (context-owned); copied to shared memory once per CTA
@@ -90,33 +90,42 @@ struct TcProg {
 // instruction descriptor becomes an immediate, and issuing a step costs no table loads.  The host builds the same
 // tables again from the packing script (tc_build, which also produces the weight images) and tc_program_matches()
 // refuses to run if the two ever disagree.
-struct TcSpecC { int step, layer, slot, col0, d_col, accum, ncols; };
+struct TcSpecC { int step, layer, slot, col0, d_col, accum, ncols, share; };   // share = k > 0: reuse the weight block of the op k specs earlier
 constexpr int kLayerOut[L_COUNT] = {10, 3, 64, 64, 10, 3, 8, 8, 128, 128, 120, 64, 64, 64, 2, 24, 96, 6, 96, 40,
                                     16, 40, 64, 32, 32, 33, 32, 1, 16, 8, 1};
 constexpr TcSpecC kSpecs[] = {
-    {ST_G1, L_GEO_AT0, 0, 0, 0, 0, 64}, {ST_G1, L_GEO_AT0, 1, 0, 0, 1, 64}, {ST_G1, L_GEO_AT0, 2, 0, 0, 1, 64}, {ST_G1, L_GEO_AT0, 3, 0, 0, 1, 16},
-    {ST_G1, L_GEO8_AT0, 3, 16, 16, 0, 32},
-    {ST_G2, L_GEO_AT1, 3, 48, 0, 0, 16}, {ST_G2, L_GEO8_AT1, 4, 0, 16, 0, 16},
-    {ST_G3, L_GEO_F0, 0, 0, 0, 0, 64}, {ST_G3, L_GEO_F0, 1, 0, 0, 1, 64}, {ST_G3, L_GEO_F0, 2, 0, 0, 1, 64}, {ST_G3, L_GEO_F0, 3, 0, 0, 1, 16},
-    {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32},
-    {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16},
-    {ST_M0, L_MLP0, 0, 0, 0, 0, 64},
-    {ST_P0, L_MLP0, 1, 0, 0, 1, 64}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64}, {ST_P2, L_MLP0, 4, 0, 0, 1, 64},
-    {ST_P3, L_MLP0, 1, 0, 0, 1, 64}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64}, {ST_P5, L_MLP0, 4, 0, 0, 1, 16},
-    {ST_M1, L_MLP1, 1, 0, 0, 0, 64}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64},
-    {ST_M2, L_MLP2, 4, 0, 0, 0, 64}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16},
-    {ST_M3, L_MLP3, 1, 0, 0, 0, 64}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64},
-    {ST_Q1, L_POST0, 1, 0, 0, 0, 64}, {ST_Q1, L_POST0, 2, 0, 0, 1, 64}, {ST_Q1, L_COMPRESS, 1, 0, 64, 0, 64}, {ST_Q1, L_COMPRESS, 2, 0, 64, 1, 64},
-    {ST_Q2, L_POST1, 4, 0, 0, 0, 64},
-    {ST_Q3, L_POST2, 0, 0, 0, 0, 64},
-    {ST_T1, L_TEX_AT0, 1, 0, 0, 0, 64}, {ST_T1, L_TEX_AT0, 2, 0, 0, 1, 32}, {ST_T1, L_RAY0, 3, 0, 96, 0, 16},
-    {ST_T2, L_TEX_AT1, 4, 0, 0, 0, 64}, {ST_T2, L_TEX_AT1, 0, 0, 0, 1, 32}, {ST_T2, L_RAY1, 3, 16, 16, 0, 16},
-    {ST_T3, L_TEX_F0, 1, 0, 0, 0, 64}, {ST_T3, L_TEX_F0, 2, 0, 0, 1, 32},
-    {ST_T4, L_TEX_F1, 4, 0, 0, 0, 64}, {ST_T4, L_TEX_F1, 0, 0, 0, 1, 32},
-    {ST_I1, L_BASE0, 1, 0, 0, 0, 64}, {ST_I1, L_BASE0, 2, 0, 0, 1, 64},
-    {ST_I2, L_BASE1, 4, 0, 0, 0, 64},
-    {ST_I3, L_VIS1_0, 0, 0, 0, 0, 32}, {ST_I4, L_VIS1_1, 0, 32, 0, 0, 32}, {ST_I5, L_VIS2_0, 0, 0, 0, 0, 32}, {ST_I6, L_VIS2_1, 0, 32, 0, 0, 32},
-    {ST_I7, L_OUT0, 3, 0, 0, 0, 48}, {ST_I8, L_OUT1, 3, 48, 0, 0, 16}, {ST_I9, L_OUT2, 0, 0, 0, 0, 16},
+    {ST_G1, L_GEO_AT0, 0, 0, 0, 0, 64, 0}, {ST_G1, L_GEO_AT0, 1, 0, 0, 1, 64, 0}, {ST_G1, L_GEO_AT0, 2, 0, 0, 1, 64, 0}, {ST_G1, L_GEO_AT0, 3, 0, 0, 1, 16, 0},
+    {ST_G1, L_GEO8_AT0, 3, 16, 16, 0, 32, 0},
+    {ST_G2, L_GEO_AT1, 3, 48, 0, 0, 16, 0}, {ST_G2, L_GEO8_AT1, 4, 0, 16, 0, 16, 0},
+    {ST_G3, L_GEO_F0, 0, 0, 0, 0, 64, 0}, {ST_G3, L_GEO_F0, 1, 0, 0, 1, 64, 0}, {ST_G3, L_GEO_F0, 2, 0, 0, 1, 64, 0}, {ST_G3, L_GEO_F0, 3, 0, 0, 1, 16, 0},
+    {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32, 0},
+    {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64, 0}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16, 0},
+    {ST_M0, L_MLP0, 0, 0, 0, 0, 64, 0},
+    {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P2, L_MLP0, 4, 0, 0, 1, 64, 0},
+    {ST_P3, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P5, L_MLP0, 4, 0, 0, 1, 16, 0},
+    {ST_M1, L_MLP1, 1, 0, 0, 0, 64, 0}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64, 0},
+    {ST_M2, L_MLP2, 4, 0, 0, 0, 64, 0}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64, 0}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16, 0},
+    {ST_M3, L_MLP3, 1, 0, 0, 0, 64, 0}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64, 0},
+    {ST_Q1, L_POST0, 1, 0, 0, 0, 64, 0}, {ST_Q1, L_POST0, 2, 0, 0, 1, 64, 0}, {ST_Q1, L_COMPRESS, 1, 0, 64, 0, 64, 0}, {ST_Q1, L_COMPRESS, 2, 0, 64, 1, 64, 0},
+    {ST_Q2, L_POST1, 4, 0, 0, 0, 64, 0},
+    {ST_Q3, L_POST2, 0, 0, 0, 0, 64, 0},
+    {ST_T1, L_TEX_AT0, 1, 0, 0, 0, 64, 0}, {ST_T1, L_TEX_AT0, 2, 0, 0, 1, 32, 0}, {ST_T1, L_RAY0, 3, 0, 96, 0, 16, 0},
+    {ST_T2, L_TEX_AT1, 4, 0, 0, 0, 64, 0}, {ST_T2, L_TEX_AT1, 0, 0, 0, 1, 32, 0}, {ST_T2, L_RAY1, 3, 16, 16, 0, 16, 0},
+    {ST_T3, L_TEX_F0, 1, 0, 0, 0, 64, 0}, {ST_T3, L_TEX_F0, 2, 0, 0, 1, 32, 0},
+    {ST_T4, L_TEX_F1, 4, 0, 0, 0, 64, 0}, {ST_T4, L_TEX_F1, 0, 0, 0, 1, 32, 0},
+    // IBR head, the three views in one step: view v works in slot 2 + v and accumulator columns stride * v; views 1, 2
+    // reuse the weight blocks of view 0 (share = distance back to the op that owns the block)
+    {ST_I1, L_BASE0, 1, 0, 0, 0, 64, 0}, {ST_I1, L_BASE0, 2, 0, 0, 1, 64, 0},
+    {ST_I1, L_BASE0, 1, 0, 64, 0, 64, 2}, {ST_I1, L_BASE0, 3, 0, 64, 1, 64, 2},
+    {ST_I1, L_BASE0, 1, 0, 128, 0, 64, 4}, {ST_I1, L_BASE0, 4, 0, 128, 1, 64, 4},
+    {ST_I2, L_BASE1, 2, 0, 0, 0, 64, 0}, {ST_I2, L_BASE1, 3, 0, 32, 0, 64, 1}, {ST_I2, L_BASE1, 4, 0, 64, 0, 64, 2},
+    {ST_I3, L_VIS1_0, 2, 0, 0, 0, 32, 0}, {ST_I3, L_VIS1_0, 3, 0, 48, 0, 32, 1}, {ST_I3, L_VIS1_0, 4, 0, 96, 0, 32, 2},
+    {ST_I4, L_VIS1_1, 2, 32, 0, 0, 32, 0}, {ST_I4, L_VIS1_1, 3, 32, 48, 0, 32, 1}, {ST_I4, L_VIS1_1, 4, 32, 96, 0, 32, 2},
+    {ST_I5, L_VIS2_0, 2, 0, 0, 0, 32, 0}, {ST_I5, L_VIS2_0, 3, 0, 48, 0, 32, 1}, {ST_I5, L_VIS2_0, 4, 0, 96, 0, 32, 2},
+    {ST_I6, L_VIS2_1, 2, 32, 0, 0, 32, 0}, {ST_I6, L_VIS2_1, 3, 32, 48, 0, 32, 1}, {ST_I6, L_VIS2_1, 4, 32, 96, 0, 32, 2},
+    {ST_I7, L_OUT0, 2, 0, 0, 0, 48, 0}, {ST_I7, L_OUT0, 3, 0, 16, 0, 48, 1}, {ST_I7, L_OUT0, 4, 0, 32, 0, 48, 2},
+    {ST_I8, L_OUT1, 2, 48, 0, 0, 16, 0}, {ST_I8, L_OUT1, 3, 48, 16, 0, 16, 1}, {ST_I8, L_OUT1, 4, 48, 32, 0, 16, 2},
+    {ST_I9, L_OUT2, 2, 0, 0, 0, 16, 0}, {ST_I9, L_OUT2, 3, 0, 16, 0, 16, 1}, {ST_I9, L_OUT2, 4, 0, 32, 0, 16, 2},
 };
 constexpr int kNumSpecs = (int)(sizeof(kSpecs) / sizeof(kSpecs[0]));
 
@@ -133,7 +142,8 @@ constexpr TcProg tc_make_prog() {
             if (kSpecs[q].step != s) continue;
             const int n_pad = (kLayerOut[kSpecs[q].layer] + 15) & ~15;
             const uint32_t bytes = (uint32_t)n_pad * 128;
-            if (rel < 0 || cur_bytes + bytes > TC_SLOT) {
+            const int share = kSpecs[q].share;               // > 0: the weight block of the op `share` ops earlier
+            if (!share && (rel < 0 || cur_bytes + bytes > TC_SLOT)) {
                 if (rel >= 0) P.ops[n_ops - 1].last_in_chunk = 1;
                 ++rel;
                 P.chunks[n_chunks].src_off = blob_bytes;
@@ -142,17 +152,19 @@ constexpr TcProg tc_make_prog() {
                 cur_bytes = 0;
             }
             P.ops[n_ops].a_off = (uint32_t)(kSpecs[q].slot * TC_SLOT + (kSpecs[q].col0 / 16) * 32);
-            P.ops[n_ops].b_off = cur_bytes;
+            P.ops[n_ops].b_off = share ? P.ops[n_ops - share].b_off : cur_bytes;
             P.ops[n_ops].idesc = tc::umma_idesc_bf16(128, n_pad);
             P.ops[n_ops].d_col = (uint16_t)kSpecs[q].d_col;
             P.ops[n_ops].nk = (uint8_t)(kSpecs[q].ncols / 16);
             P.ops[n_ops].accum = (uint8_t)kSpecs[q].accum;
-            P.ops[n_ops].chunk_rel = (uint8_t)rel;
+            P.ops[n_ops].chunk_rel = share ? P.ops[n_ops - share].chunk_rel : (uint8_t)rel;
             P.ops[n_ops].last_in_chunk = 0;
             ++n_ops;
-            cur_bytes += bytes;
-            blob_bytes += bytes;
-            P.chunks[n_chunks - 1].bytes = cur_bytes;
+            if (!share) {
+                cur_bytes += bytes;
+                blob_bytes += bytes;
+                P.chunks[n_chunks - 1].bytes = cur_bytes;
+            }
         }
         if (n_ops > P.steps[s].op0) P.ops[n_ops - 1].last_in_chunk = 1;
         P.steps[s].nops = (uint16_t)(n_ops - P.steps[s].op0);
@@ -178,6 +190,7 @@ constexpr TcProg kProg = tc_make_prog();
 struct TcOpSpec {
     int layer, a_slot, a_col0, d_col, accum;
     std::vector<int> kmap;       // per operand column: input index of the reference layer, -1 = zero weight
+    int share = 0;               // > 0: reuse the weight block of the op `share` ops earlier (same step)
 };
 
 static std::vector<int> iota_map(int from, int n, int pad_to = -1) {
@@ -195,8 +208,8 @@ static const int kTexMap2[32] = {69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80,
 
 static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
     st.assign(ST_COUNT, {});
-    auto add = [&](int s, int layer, int slot, int col0, int d_col, int accum, std::vector<int> kmap) {
-        st[s].push_back(TcOpSpec{layer, slot, col0, d_col, accum, std::move(kmap)});
+    auto add = [&](int s, int layer, int slot, int col0, int d_col, int accum, std::vector<int> kmap, int share = 0) {
+        st[s].push_back(TcOpSpec{layer, slot, col0, d_col, accum, std::move(kmap), share});
     };
     std::vector<int> tex1(kTexMap1, kTexMap1 + 64), tex2(kTexMap2, kTexMap2 + 32);
     // ---- GeoVisFusion, both scales side by side (src/networks.py:83-104)
@@ -248,20 +261,21 @@ static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
         add(s, l, 0, 0, 0, 1, iota_map(64, 32));
     }
     add(ST_T2, L_RAY1, 3, 16, 16, 0, iota_map(0, 16));
-    // ---- IBRRenderingHead (src/model.py:1600-1636): base input [mean 40 | var 40 | f 40]
-    {
-        std::vector<int> m2 = iota_map(64, 56, 64);
-        add(ST_I1, L_BASE0, 1, 0, 0, 0, iota_map(0, 64));
-        add(ST_I1, L_BASE0, 2, 0, 0, 1, m2);
+    // ---- IBRRenderingHead (src/model.py:1600-1636), the views batched in one step: view v works in slot 2 + v and
+    // accumulator columns stride * v, views 1, 2 reuse view 0's weight blocks.  base input [mean 40 | var 40 | f 40]:
+    // slot 1 = [mean 40 | var 0..23] (shared), slot 2 + v = [var 24..39 | f_v 40 | pad 8]
+    for (int v = 0; v < TC_MAXV; ++v) {
+        add(ST_I1, L_BASE0, 1, 0, 64 * v, 0, iota_map(0, 64), 2 * v);
+        add(ST_I1, L_BASE0, 2 + v, 0, 64 * v, 1, iota_map(64, 56, 64), 2 * v);
     }
-    add(ST_I2, L_BASE1, 4, 0, 0, 0, iota_map(0, 64));
-    add(ST_I3, L_VIS1_0, 0, 0, 0, 0, iota_map(0, 32));
-    add(ST_I4, L_VIS1_1, 0, 32, 0, 0, iota_map(0, 32));
-    add(ST_I5, L_VIS2_0, 0, 0, 0, 0, iota_map(0, 32));
-    add(ST_I6, L_VIS2_1, 0, 32, 0, 0, iota_map(0, 32));
-    add(ST_I7, L_OUT0, 3, 0, 0, 0, iota_map(0, 37, 48));
-    add(ST_I8, L_OUT1, 3, 48, 0, 0, iota_map(0, 16));
-    add(ST_I9, L_OUT2, 0, 0, 0, 0, iota_map(0, 8, 16));
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I2, L_BASE1, 2 + v, 0, 32 * v, 0, iota_map(0, 64), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I3, L_VIS1_0, 2 + v, 0, 48 * v, 0, iota_map(0, 32), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I4, L_VIS1_1, 2 + v, 32, 48 * v, 0, iota_map(0, 32), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I5, L_VIS2_0, 2 + v, 0, 48 * v, 0, iota_map(0, 32), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I6, L_VIS2_1, 2 + v, 32, 48 * v, 0, iota_map(0, 32), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I7, L_OUT0, 2 + v, 0, 16 * v, 0, iota_map(0, 37, 48), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I8, L_OUT1, 2 + v, 48, 16 * v, 0, iota_map(0, 16), v);
+    for (int v = 0; v < TC_MAXV; ++v) add(ST_I9, L_OUT2, 2 + v, 0, 16 * v, 0, iota_map(0, 8, 16), v);
 }
 
 static inline uint16_t f2bf_host(float f) {
@@ -290,7 +304,7 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
             const int n_pad = (L.out_dim + 15) & ~15;
             const int ncols = (int)o.kmap.size();
             const uint32_t bytes = (uint32_t)n_pad * 128;
-            if (rel < 0 || cur_bytes + bytes > TC_SLOT) {          // open a new chunk
+            if (!o.share && (rel < 0 || cur_bytes + bytes > TC_SLOT)) {          // open a new chunk
                 if (rel >= 0) P.ops[n_ops - 1].last_in_chunk = 1;
                 ++rel;
                 P.chunks[n_chunks].src_off = (uint32_t)(blob.size() * 2);
@@ -300,13 +314,14 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
             }
             TcOp& d = P.ops[n_ops++];
             d.a_off = (uint32_t)(o.a_slot * TC_SLOT + (o.a_col0 / 16) * 32);
-            d.b_off = cur_bytes;
+            d.b_off = o.share ? P.ops[n_ops - 1 - o.share].b_off : cur_bytes;
             d.idesc = tc::umma_idesc_bf16(128, n_pad);
             d.d_col = (uint16_t)o.d_col;
             d.nk = (uint8_t)(ncols / 16);
             d.accum = (uint8_t)o.accum;
-            d.chunk_rel = (uint8_t)rel;
+            d.chunk_rel = o.share ? P.ops[n_ops - 1 - o.share].chunk_rel : (uint8_t)rel;
             d.last_in_chunk = 0;
+            if (o.share) continue;                                               // weights already in the chunk
             const size_t base = blob.size();
             blob.resize(base + bytes / 2, 0);
             for (int n = 0; n < L.out_dim; ++n)
@@ -814,11 +829,10 @@ __device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs)
         cc += cc_q;
 #pragma unroll 1
         for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
-#pragma unroll 1
-        for (int v = 0; v < V; ++v, cc += cc_i) {
-            ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
-            ISTEP(ST_I8, 0); ISTEP(ST_I9, 0);
-        }
+        // the rendering head runs once per tile for all views
+        ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
+        ISTEP(ST_I8, 0); ISTEP(ST_I9, 0);
+        cc += cc_i;
     }
 #undef ISTEP
 }
@@ -854,10 +868,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 LSTEP(ST_Q1); LSTEP(ST_Q2); LSTEP(ST_Q3);
 #pragma unroll 1
                 for (int v = 0; v < V; ++v) { LSTEP(ST_T1); LSTEP(ST_T2); LSTEP(ST_T3); LSTEP(ST_T4); }
-#pragma unroll 1
-                for (int v = 0; v < V; ++v) {
-                    LSTEP(ST_I1); LSTEP(ST_I2); LSTEP(ST_I3); LSTEP(ST_I4); LSTEP(ST_I5); LSTEP(ST_I6); LSTEP(ST_I7); LSTEP(ST_I8); LSTEP(ST_I9);
-                }
+                LSTEP(ST_I1); LSTEP(ST_I2); LSTEP(ST_I3); LSTEP(ST_I4); LSTEP(ST_I5); LSTEP(ST_I6); LSTEP(ST_I7); LSTEP(ST_I8); LSTEP(ST_I9);
             }
 #undef LSTEP
         }
@@ -1168,6 +1179,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll
                 for (int v = 0; v < TC_MAXV; ++v) if (v < V) wt[v] = e[v] / (sum + 1e-8f);
             }
+            // source colours of the views leave TMEM now: the batched steps below use accumulator columns 0..191
+            float srcc[3 * TC_MAXV];
+            {
+                float s16[16];
+                t.ld16(TC_SRC, s16);
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) srcc[3 * v + c] = s16[4 * v + c];
+            }
+            // The nine steps of the head run ONCE per tile for all views: view v has its own operand slot (2 + v), its own
+            // accumulator columns (stride 64 / 32 / 48 / 16 per step) and its residual x in TMEM columns 160 + 32 v; the
+            // weights are shared.  Layout of slot 2 + v over the steps: I1 in [var 24..39 | f_v | pad], I2 in ELU(base0) 64,
+            // I3 / I5 in cols 0..31, I4 / I6 in cols 32..63, I7 in cols 0..47, I8 in cols 48..63, I9 in cols 0..15.
             {   // fused_mean_variance (src/utils.py:153-157): channels 0..23 (h=0) / 24..39 (h=1), 8 at a time;
                 // each thread reads back only the f columns it stored itself
                 const int g0 = h ? 3 : 0, g1 = h ? 5 : 3;
@@ -1194,77 +1219,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     }
                     t.st_chunk(1, g, pack8(mean));                               // mean -> slot 1 cols 0..39
                     if (g < 3) t.st_chunk(1, 5 + g, pack8(var));                 // var 0..23 -> slot 1 cols 40..63
-                    else t.st_chunk(2, g - 3, pack8(var));                       // var 24..39 -> slot 2 cols 0..15
-                }
-                if (h == 1) t.st_chunk(2, 7, make_uint4(0, 0, 0, 0));
-            }
 #pragma unroll
-            for (int v = 0; v < TC_MAXV; ++v) {
-                if (v >= V) break;
-                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
-                {   // f_v -> slot 2 cols 16..55
-                    const int g0 = h ? 3 : 0, g1 = h ? 5 : 3;
-#pragma unroll 1
-                    for (int g = g0; g < g1; ++g) {
-                        float f[8];
-                        t.ld8(TC_SREG + 40 * v + 8 * g, f);
-                        t.st_chunk(2, 2 + g, pack8(f));
+                    for (int v = 0; v < TC_MAXV; ++v) {
+                        if (v < V) {
+                            if (g >= 3) t.st_chunk(2 + v, g - 3, pack8(var));    // var 24..39 -> slot 2+v cols 0..15
+                            t.st_chunk(2 + v, 2 + g, pack8(f[v]));               // f_v -> slot 2+v cols 16..55
+                        }
                     }
                 }
-                t.step(ST_I1);
-                EPI(TA_ELU, 32 * h, 2, BIASP(L_BASE0) + 32 * h, 4, 4 * h);
-                t.step(ST_I2);
-                float x[16];
-                t.ld16(16 * h, x);
+                if (h == 1) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_BASE1)[16 * h + i]);
-                {
-                    float y[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = x[i] * wt[v];
-                    t.st_chunk(0, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
-                    t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                    for (int v = 0; v < TC_MAXV; ++v) if (v < V) t.st_chunk(2 + v, 7, make_uint4(0, 0, 0, 0));
                 }
-                t.step(ST_I3);
-                EPI(TA_ELU, 16 * h, 1, BIASP(L_VIS1_0) + 16 * h, 0, 4 + 2 * h);
-                t.step(ST_I4);
-                {
-                    float r[16], vv[8];
-                    t.ld16(16 * h, r);
-                    t.ld8(32, vv);
+            }
+            // all reads of the f columns precede the accumulator writes of I1 (ordered by the step's publish)
+            t.step(ST_I1);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v)
+                if (v < V) tc_epi_store<TA_ELU, 2>(t, 64 * v + 32 * h, BIASP(L_BASE0) + 32 * h, t.slot(2 + v), 4 * h);
+            t.step(ST_I2);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v) {
+                if (v < V) {
+                    float x[16], y[16];
+                    t.ld16(32 * v + 16 * h, x);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_BASE1)[16 * h + i]);
+                        y[i] = x[i] * wt[v];
+                    }
+                    t.st16(160 + 32 * v + 16 * h, x);
+                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
+                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                }
+            }
+            tc::tmem_st_wait();
+            t.step(ST_I3);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v)
+                if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS1_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
+            t.step(ST_I4);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v) {
+                if (v < V) {
+                    float r[16], vv[8], x[16], y[16];
+                    t.ld16(48 * v + 16 * h, r);
+                    t.ld8(48 * v + 32, vv);
+                    t.ld16(160 + 32 * v + 16 * h, x);
                     const float vis = tc_act<TA_SIGMOID>(tc_act<TA_ELU>(vv[0] + BIASP(L_VIS1_1)[32])) * maskv;
-                    float y[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         x[i] += tc_act<TA_ELU>(r[i] + BIASP(L_VIS1_1)[16 * h + i]);
                         y[i] = x[i] * vis;
                     }
-                    t.st_chunk(0, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
-                    t.st_chunk(0, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                    t.st16(160 + 32 * v + 16 * h, x);
+                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
+                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
                 }
-                t.step(ST_I5);
-                EPI(TA_ELU, 16 * h, 1, BIASP(L_VIS2_0) + 16 * h, 0, 4 + 2 * h);
-                t.step(ST_I6);
-                {
-                    float vv[8];
-                    t.ld8(0, vv);
+            }
+            tc::tmem_st_wait();
+            t.step(ST_I5);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v)
+                if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
+            t.step(ST_I6);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v) {
+                if (v < V) {
+                    float vv[8], x[16];
+                    t.ld8(48 * v, vv);
+                    t.ld16(160 + 32 * v + 16 * h, x);
                     const float vis2 = tc_act<TA_SIGMOID>(vv[0] + BIASP(L_VIS2_1)[0]) * maskv;
-                    // out_layer input [x 32 | vis | ray_diff 4] -> slot 3 cols 0..47
-                    t.st_chunk(3, 2 * h, make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7])));
-                    t.st_chunk(3, 2 * h + 1, make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15])));
-                    if (h == 0) t.st_chunk(3, 4, make_uint4(tc::pack_bf16(vis2, a0.w), tc::pack_bf16(a1.x, a1.y), tc::pack_bf16(a1.z, 0.f), 0));
-                    else t.st_chunk(3, 5, make_uint4(0, 0, 0, 0));
+                    // out_layer input [x 32 | vis | ray_diff 4] -> slot 2+v cols 0..47
+                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7])));
+                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15])));
+                    if (h == 0) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
+                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                        t.st_chunk(2 + v, 4, make_uint4(tc::pack_bf16(vis2, a0.w), tc::pack_bf16(a1.x, a1.y), tc::pack_bf16(a1.z, 0.f), 0));
+                    } else {
+                        t.st_chunk(2 + v, 5, make_uint4(0, 0, 0, 0));
+                    }
                 }
-                t.step(ST_I7);
-                if (h == 0) EPI(TA_ELU, 0, 1, BIASP(L_OUT0), 3, 6);
-                t.step(ST_I8);
-                if (h == 0) EPI(TA_ELU, 0, 1, BIASP(L_OUT1), 0, 0);
-                t.step(ST_I9);
-                {
-                    float vv[8];
-                    t.ld8(0, vv);
-                    sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + BIASP(L_OUT2)[0]);
+            }
+            t.step(ST_I7);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
+                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
+            t.step(ST_I8);
+#pragma unroll
+            for (int v = 0; v < TC_MAXV; ++v)
+                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
+            t.step(ST_I9);
+            if (h == 0) {
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    if (v < V) {
+                        float vv[8];
+                        t.ld8(16 * v, vv);
+                        sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + BIASP(L_OUT2)[0]);
+                    }
                 }
             }
             // =========================================================== softmax blend + eval_func (src/model.py:1634-1635, 1140-1160)
@@ -1273,15 +1327,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll
                 for (int v = 0; v < TC_MAXV; ++v) if (v < V) smax = fmaxf(smax, sv[v]);
                 float den = 0.f, rgb[3] = {0.f, 0.f, 0.f};
-                float src[16];
-                t.ld16(TC_SRC, src);
 #pragma unroll
                 for (int v = 0; v < TC_MAXV; ++v) {
                     if (v < V) {
                         const float e = __expf(sv[v] - smax);
                         den += e;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) rgb[c] += src[4 * v + c] * e;
+                        for (int c = 0; c < 3; ++c) rgb[c] += srcc[3 * v + c] * e;
                     }
                 }
                 const float inv = 1.0f / den;
