@@ -499,7 +499,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
 // Issues op I (and the following ones) of step ST: everything but the ring slot of the weight chunk is an immediate.
 // Whole warp, converged; `lead` = the elected lane that executes the MMAs and commits.
 template <int ST, int I>
-__device__ __forceinline__ void tc_issue_op(uint32_t cc, uint32_t slot_i, TcShared* sh, uint32_t act_u32, uint32_t ring_u32,
+__device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint32_t slot_i, TcShared* sh, uint64_t ad_base, uint64_t bd_base,
                                             uint32_t tmem, bool lead) {
     constexpr TcStep S = kProg.steps[ST];
     constexpr TcOp op = kProg.ops[S.op0 + I];
@@ -507,21 +507,23 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint32_t slot_i, TcShar
     if (first_in_chunk) {
         const uint32_t c = cc + op.chunk_rel;
         slot_i = c % TC_NRING;
+        bd_slot = bd_base + (uint64_t)(slot_i * (TC_SLOT >> 4));
         TC_PROF(7000);
         tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
         tc::tcgen05_fence_after();
         TC_PROF(7100);
     }
-    // descriptors are formed outside the elected-lane branch so that they stay on the uniform datapath
-    const uint64_t ad = tc_desc(act_u32 + op.a_off);
-    const uint64_t bd = tc_desc(ring_u32 + slot_i * TC_SLOT + op.b_off);
+    // descriptors = base descriptor + (byte offset >> 4): the start-address field (14 bits of address >> 4) cannot
+    // carry into its neighbours because every operand lies inside the CTA's 227 KB of shared memory
+    const uint64_t ad = ad_base + (uint64_t)(op.a_off >> 4);
+    const uint64_t bd = bd_slot + (uint64_t)(op.b_off >> 4);
     if (lead) {
 #pragma unroll
         for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
             tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
         if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
     }
-    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1>(cc, slot_i, sh, act_u32, ring_u32, tmem, lead);
+    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1>(cc, bd_slot, slot_i, sh, ad_base, bd_base, tmem, lead);
 }
 // One step of an MMA issuer warp: wait until the tile's eight warps have published the operands of step number n
 // (and finished reading the accumulators the step overwrites), then issue the step's MMAs and commit.
@@ -540,7 +542,7 @@ __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, Tc
     // kernel is draining and results are discarded): otherwise the compiler computes the descriptors of all 140-odd
     // MMAs ahead of the waits and spills them to local memory.
     const uint32_t never = ok ? 0u : 16u;
-    tc_issue_op<ST, 0>(cc_base + cc_off, 0, sh, act_u32 + never, ring_u32 + never, tmem, lead);
+    tc_issue_op<ST, 0>(cc_base + cc_off, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead);
     if (lead) {
         if (COMMIT == 0) tc::umma_commit(&sh->acc_bar[tg]);
         else if (COMMIT > 0) tc::umma_commit(&sh->pfree[tg][COMMIT > 0 ? COMMIT - 1 : 0]);
