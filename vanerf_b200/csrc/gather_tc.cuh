@@ -164,6 +164,16 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             *reinterpret_cast<uint4*>(img + off) = tap8_bf16(ft.geo0 + (size_t)v * fr.g0h * fr.g0w * 64, 64, 8 * lane, b64);
             *reinterpret_cast<uint4*>(img + TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + nn) * 64 + 8 * lane);
             *reinterpret_cast<uint4*>(img + 2 * TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + tw) * 64 + 8 * lane);
+            // the two 8-channel bilinear taps (geo1 on lane 2, tex on lane 0) run as ONE code path with per-lane map
+            // parameters: a warp executes every divergent branch body, so two separate branches would cost twice
+            uint4 tap8c = make_uint4(0, 0, 0, 0);
+            if (lane == 0 || lane == 2) {
+                const bool g = lane == 2;
+                const int mw = g ? fr.g1w : fr.tw, mh = g ? fr.g1h : fr.th;
+                const __nv_bfloat16* mp = g ? ft.geo1 + (size_t)v * fr.g1h * fr.g1w * 8 : ft.tex + (size_t)v * fr.th * fr.tw * 8;
+                const Bilin b = bilin_setup(x, y, mw, mh);
+                tap8c = tap8_bf16(mp, 8, 0, b);
+            }
             // R3 (misc): c0 [sdf,qvis,vn,vt,0..] | c1 0 | c2 px8 | c3 a8 | c4 b8 | c5 [sdf,qvis,vn,vt,0..] | c6,c7 0
             {
                 uint4 o = make_uint4(0, 0, 0, 0);
@@ -171,8 +181,7 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
                     o.x = tc::pack_bf16(sdfv, qv);
                     o.y = tc::pack_bf16(vn, vt);
                 } else if (lane == 2) {
-                    const Bilin b = bilin_setup(x, y, fr.g1w, fr.g1h);
-                    o = tap8_bf16(ft.geo1 + (size_t)v * fr.g1h * fr.g1w * 8, 8, 0, b);
+                    o = tap8c;
                 } else if (lane == 3) {
                     o = *reinterpret_cast<const uint4*>(ft.T8 + (vb + nn) * 8);
                 } else if (lane == 4) {
@@ -185,10 +194,8 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
                 uint4 o;
                 const __nv_bfloat16* ta = ft.Ttex + (vb + nn) * 32;
                 const __nv_bfloat16* tb = ft.Ttex + (vb + tw) * 32;
-                if (lane == 0) {
-                    const Bilin b = bilin_setup(x, y, fr.tw, fr.th);
-                    o = tap8_bf16(ft.tex + (size_t)v * fr.th * fr.tw * 8, 8, 0, b);
-                } else if (lane == 1) o = *reinterpret_cast<const uint4*>(ta);
+                if (lane == 0) o = tap8c;
+                else if (lane == 1) o = *reinterpret_cast<const uint4*>(ta);
                 else if (lane == 2) o = *reinterpret_cast<const uint4*>(tb);
                 else if (lane == 3) o = *reinterpret_cast<const uint4*>(ta + 8);
                 else if (lane == 4) o = *reinterpret_cast<const uint4*>(ta + 16);
@@ -209,23 +216,20 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             // side record
             if (lane < 4) {
                 uint4 o;
-                if (lane == 0) {
-                    const float* E = fr.extrin[v];
+                if (lane < 2) {        // lanes 0 and 1 share the direction normalisations (one code path)
                     float s0 = p[0] - fr.src_pos[v][0], s1 = p[1] - fr.src_pos[v][1], s2 = p[2] - fr.src_pos[v][2];
                     const float inv = 1.0f / fmaxf(sqrtf(s0 * s0 + s1 * s1 + s2 * s2), 1e-12f);
                     s0 *= inv; s1 *= inv; s2 *= inv;
                     const float e0 = ray[0] - s0, e1 = ray[1] - s1, e2 = ray[2] - s2;
                     const float ninv = 1.0f / fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-6f);
-                    o = make_uint4(__float_as_uint(xaffine(E, 0, p[0], p[1], p[2])), __float_as_uint(xaffine(E, 1, p[0], p[1], p[2])),
-                                   __float_as_uint(xaffine(E, 2, p[0], p[1], p[2])), __float_as_uint(e0 * ninv));
-                } else if (lane == 1) {
-                    float s0 = p[0] - fr.src_pos[v][0], s1 = p[1] - fr.src_pos[v][1], s2 = p[2] - fr.src_pos[v][2];
-                    const float inv = 1.0f / fmaxf(sqrtf(s0 * s0 + s1 * s1 + s2 * s2), 1e-12f);
-                    s0 *= inv; s1 *= inv; s2 *= inv;
-                    const float e0 = ray[0] - s0, e1 = ray[1] - s1, e2 = ray[2] - s2;
-                    const float ninv = 1.0f / fmaxf(sqrtf(e0 * e0 + e1 * e1 + e2 * e2), 1e-6f);
-                    o = make_uint4(__float_as_uint(e1 * ninv), __float_as_uint(e2 * ninv),
-                                   __float_as_uint(s0 * ray[0] + s1 * ray[1] + s2 * ray[2]), __float_as_uint(pw[v] / (pw_sum + 1e-6f)));
+                    if (lane == 0) {
+                        const float* E = fr.extrin[v];
+                        o = make_uint4(__float_as_uint(xaffine(E, 0, p[0], p[1], p[2])), __float_as_uint(xaffine(E, 1, p[0], p[1], p[2])),
+                                       __float_as_uint(xaffine(E, 2, p[0], p[1], p[2])), __float_as_uint(e0 * ninv));
+                    } else {
+                        o = make_uint4(__float_as_uint(e1 * ninv), __float_as_uint(e2 * ninv),
+                                       __float_as_uint(s0 * ray[0] + s1 * ray[1] + s2 * ray[2]), __float_as_uint(pw[v] / (pw_sum + 1e-6f)));
+                    }
                 } else if (lane == 2) {
                     o = make_uint4(__float_as_uint(mf), 0, 0, 0);
                 } else {
