@@ -75,7 +75,7 @@ __device__ __forceinline__ uint4 tap8_bf16(const __nv_bfloat16* __restrict__ map
 
 // rec: (n_tiles, V, 5, 16 KB) operand images; aux: (n_tiles*128, V, 64 B).  Rows past n_chunk in the last tile are
 // written as copies of the last sample (finite values; their outputs are never stored).
-__global__ void __launch_bounds__(GTC_THREADS)
+__global__ void __launch_bounds__(GTC_THREADS, 3)
 k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
             const float* __restrict__ pts_in, const float* __restrict__ view_in, int S, long long sample0, int n_chunk,
             long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,
@@ -101,7 +101,7 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
         // ---- pass 1, one lane per view (lane v < V of the sample's 8 lanes; the same exact-op sequence as before,
         // just not repeated by all 8 lanes): projection, in-frustum and foreground masks, boundary weight, and the
         // bilinear tap set of the 64-channel map; the results are shared with 8-wide shuffles.
-        float mx = 0.f, my = 0.f, mw = 0.f;
+        float mx = 0.f, my = 0.f, mw = 0.f, mcr = 0.f, mcg = 0.f, mcb = 0.f;
         int mok = 1;
         Bilin mb;
         mb.i00 = mb.i01 = mb.i10 = mb.i11 = 0; mb.nw = mb.ne = mb.sw = mb.se = 0.f;
@@ -109,9 +109,14 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             const int v = lane;
             const ViewProj q = project_sample(fr, v, p);
             const Bilin b = bilin_setup(q.x, q.y, fr.W, fr.H);
-            const float* mp = fr.imgm + (size_t)v * fr.H * fr.W * 4 + 3;
-            const float fgv = bilin_mix(b, mp[(size_t)b.i00 * 4], b.i01 >= 0 ? mp[(size_t)b.i01 * 4] : 0.f,
-                                        b.i10 >= 0 ? mp[(size_t)b.i10 * 4] : 0.f, b.i11 >= 0 ? mp[(size_t)b.i11 * 4] : 0.f);
+            // the image tap (r, g, b) reads the same four texels as the foreground-mask tap: do both here
+            const float4* ip = reinterpret_cast<const float4*>(fr.imgm) + (size_t)v * fr.H * fr.W;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 t00 = ip[b.i00], t01 = b.i01 >= 0 ? ip[b.i01] : z4, t10 = b.i10 >= 0 ? ip[b.i10] : z4, t11 = b.i11 >= 0 ? ip[b.i11] : z4;
+            const float fgv = bilin_mix(b, t00.w, t01.w, t10.w, t11.w);
+            mcr = bilin_mix(b, t00.x, t01.x, t10.x, t11.x);
+            mcg = bilin_mix(b, t00.y, t01.y, t10.y, t11.y);
+            mcb = bilin_mix(b, t00.z, t01.z, t10.z, t11.z);
             mok = (q.in && fgv > 0.1f) ? 1 : 0;
             float w = 1.0f;
             const float q3[3] = {q.x, q.y, q.zn};
@@ -153,6 +158,7 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             if (v >= V) break;
             unsigned char* img = rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
             const float x = __shfl_sync(0xffffffffu, mx, v, 8), y = __shfl_sync(0xffffffffu, my, v, 8);
+            const float cr = __shfl_sync(0xffffffffu, mcr, v, 8), cg = __shfl_sync(0xffffffffu, mcg, v, 8), cb = __shfl_sync(0xffffffffu, mcb, v, 8);
             Bilin b64;
             b64.i00 = __shfl_sync(0xffffffffu, mb.i00, v, 8); b64.i01 = __shfl_sync(0xffffffffu, mb.i01, v, 8);
             b64.i10 = __shfl_sync(0xffffffffu, mb.i10, v, 8); b64.i11 = __shfl_sync(0xffffffffu, mb.i11, v, 8);
@@ -195,21 +201,17 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
                 const __nv_bfloat16* ta = ft.Ttex + (vb + nn) * 32;
                 const __nv_bfloat16* tb = ft.Ttex + (vb + tw) * 32;
                 if (lane == 0) o = tap8c;
-                else if (lane == 1) o = *reinterpret_cast<const uint4*>(ta);
-                else if (lane == 2) o = *reinterpret_cast<const uint4*>(tb);
-                else if (lane == 3) o = *reinterpret_cast<const uint4*>(ta + 8);
-                else if (lane == 4) o = *reinterpret_cast<const uint4*>(ta + 16);
-                else if (lane == 5) o = *reinterpret_cast<const uint4*>(tb + 8);
-                else if (lane == 6) o = *reinterpret_cast<const uint4*>(tb + 16);
-                else {
+                else if (lane < 7) {       // lanes 1..6: one row chunk each, a per-lane pointer instead of six branches
+                    const __nv_bfloat16* rowp = (lane == 1 || lane == 3 || lane == 4) ? ta : tb;
+                    const int coff = lane < 3 ? 0 : ((lane == 3 || lane == 5) ? 8 : 16);
+                    o = *reinterpret_cast<const uint4*>(rowp + coff);
+                } else {
                     const uint4 qa = *reinterpret_cast<const uint4*>(ta + 24);      // gf16, gf17, r, g, b, 0,0,0
                     const uint4 qb = *reinterpret_cast<const uint4*>(tb + 24);
-                    const Bilin b = bilin_setup(x, y, fr.W, fr.H);
-                    const float4 c = tap4(fr.imgm + (size_t)v * fr.H * fr.W * 4, 4, 0, b);
                     o.x = qa.x;                                                      // agf16, agf17
                     o.y = qb.x;                                                      // bgf16, bgf17
-                    o.z = tc::pack_bf16(c.x, c.y);                                   // q r, g
-                    o.w = tc::pack_bf16(c.z, __uint_as_float(qa.y << 16));           // q b, a r
+                    o.z = tc::pack_bf16(cr, cg);                                     // q r, g (tapped in pass 1)
+                    o.w = tc::pack_bf16(cb, __uint_as_float(qa.y << 16));            // q b, a r
                 }
                 *reinterpret_cast<uint4*>(img + 4 * TC_SLOT + off) = o;
             }
