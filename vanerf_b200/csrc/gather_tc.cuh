@@ -72,10 +72,13 @@ __device__ __forceinline__ uint4 tap8_bf16(const __nv_bfloat16* __restrict__ map
 }
 
 #define GTC_THREADS 256
+#ifndef GTC_MINB
+#define GTC_MINB 4                      // resident CTAs per SM the register allocation aims for
+#endif
 
 // rec: (n_tiles, V, 5, 16 KB) operand images; aux: (n_tiles*128, V, 64 B).  Rows past n_chunk in the last tile are
 // written as copies of the last sample (finite values; their outputs are never stored).
-__global__ void __launch_bounds__(GTC_THREADS, 3)
+__global__ void __launch_bounds__(GTC_THREADS, GTC_MINB)
 k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
             const float* __restrict__ pts_in, const float* __restrict__ view_in, int S, long long sample0, int n_chunk,
             long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,

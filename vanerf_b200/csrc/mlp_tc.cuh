@@ -24,7 +24,18 @@
 #include "tc_prims.cuh"
 
 #define TC_NACT 5
+// Weight ring depth.  With the tables passed as a kernel parameter (constant bank, TC_TAB_PARAM) the shared memory they
+// used to take is enough for a fourth 16 KB ring slot: a whole 3-chunk step plus the first chunk of the next one.
+#ifndef TC_TAB_PARAM
+#define TC_TAB_PARAM 1
+#endif
+#ifndef TC_NRING
+#if TC_TAB_PARAM && !defined(VANERF_TC_TRACE)
+#define TC_NRING 4
+#else
 #define TC_NRING 3
+#endif
+#endif
 #define TC_TILES 2                       // tiles in flight per CTA
 #define TC_EPI_THREADS 256               // threads of one tile group
 #define TC_THREADS (TC_TILES * TC_EPI_THREADS + 128)   // + one warpgroup: weight producer warp, one MMA issuer warp per tile, one parked warp
@@ -38,7 +49,11 @@
 #define TC_MAXV 3
 #define TC_OFF_RING (TC_TILES * TC_NACT * TC_SLOT)
 #define TC_OFF_TAB (TC_OFF_RING + TC_NRING * TC_SLOT)
+#if TC_TAB_PARAM
+#define TC_TAB_BYTES 0                   // tables live in the kernel parameter (constant bank)
+#else
 #define TC_TAB_BYTES 6656                // >= sizeof(TcTables), multiple of 16
+#endif
 #define TC_OFF_CTRL (TC_OFF_TAB + TC_TAB_BYTES)
 #define TC_OFF_TRACE (TC_OFF_CTRL + 512)
 #ifdef VANERF_TC_TRACE
@@ -48,6 +63,9 @@
 #endif
 #define TC_SMEM_BYTES (TC_OFF_TRACE + TC_TRACE_N * 8)
 
+#ifndef TC_ABLATE
+#define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
+#endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating
 enum TcStepId {
     ST_G1 = 0, ST_G2, ST_G3, ST_G4, ST_M0, ST_P0, ST_P1, ST_P2, ST_P3, ST_P4, ST_P5, ST_M1, ST_M2, ST_M3,
     ST_Q1, ST_Q2, ST_Q3, ST_T1, ST_T2, ST_T3, ST_T4, ST_I1, ST_I2, ST_I3, ST_I4, ST_I5, ST_I6, ST_I7, ST_I8, ST_I9,
@@ -382,7 +400,8 @@ static bool tc_program_matches(const TcProg& P) {
     return P.cc_gm == K.cc_gm && P.cc_q == K.cc_q && P.cc_t == K.cc_t && P.cc_i == K.cc_i;
 }
 
-static_assert(sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
+static_assert(TC_TAB_PARAM || sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
+static_assert(sizeof(TcTables) <= 8192, "TcTables travels as a kernel parameter");
 static_assert(sizeof(TcProg) <= 8192, "TcProg must stay a small part of constant memory");
 // ================================================================================================ device
 // Optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile), compiled in only with -DVANERF_TC_TRACE: entries
@@ -440,6 +459,9 @@ __device__ __forceinline__ float tc_ex2(float x) {
 template <int ACT> __device__ __forceinline__ float tc_act(float x) {
     if (ACT == TA_RELU) return fmaxf(x, 0.0f);
     if (ACT == TA_SOFTPLUS) return fmaxf(x, 0.0f) + 0.01f * __logf(1.0f + __expf(-100.0f * fabsf(x)));   // Softplus(beta=100)
+#if TC_ABLATE & 8
+    if (ACT == TA_SIGMOID || ACT == TA_ELU) return x;
+#endif
     if (ACT == TA_SIGMOID) return __fdividef(1.0f, 1.0f + tc_ex2(-1.44269504f * x));
     if (ACT == TA_ELU) return x > 0.0f ? x : tc_ex2(1.44269504f * x) - 1.0f;
     return x;
@@ -450,6 +472,10 @@ template <int ACT> __device__ __forceinline__ float tc_act(float x) {
 // Above the reference's threshold (100 x > 20) the correction is < 2.1e-11, i.e. the reference's linear branch.
 __device__ __forceinline__ uint32_t tc_softplus2(float a, float b) {
     uint32_t h, na, w, p, r;
+#if TC_ABLATE & 1
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+#endif
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
     asm("{.reg .b32 n;\n\t"
         "neg.bf16x2 n, %1;\n\t"
@@ -519,7 +545,7 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
     const uint64_t bd = bd_slot + (uint64_t)(op.b_off >> 4);
     if (lead) {
 #pragma unroll
-        for (int k = 0; k < op.nk; ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
+        for (int k = 0; k < ((TC_ABLATE & 4) ? 1 : op.nk); ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
             tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
         if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
     }
@@ -656,6 +682,9 @@ struct TcTile {
         st_chunk(s, chunk, pack8(f));
     }
     __device__ __forceinline__ void gate_chunk1(int s, int chunk, float g) const {
+#if TC_ABLATE & 16
+        return;
+#endif
         float f[8];
         unpack8(ld_chunk(s, chunk), f);
 #pragma unroll
@@ -727,11 +756,15 @@ __device__ __forceinline__ void tc_setup(unsigned char* smem, TcShared* sh, cons
 #endif
         tc::mbar_fence_init();
     }
-    {   // tables -> shared memory
+#if !TC_TAB_PARAM
+    if (tab_g) {   // tables -> shared memory
         const uint4* src = reinterpret_cast<const uint4*>(tab_g);
         uint4* dst = reinterpret_cast<uint4*>(smem + TC_OFF_TAB);
         for (int i = tid; i < (int)(sizeof(TcTables) / 16); i += blockDim.x) dst[i] = src[i];
     }
+#else
+    (void)tab_g;
+#endif
     if (warp == 0) tc::tmem_alloc(&sh->tmem_base, TC_TMEM_COLS);
     tc::tcgen05_fence_before();
     __syncthreads();
@@ -760,13 +793,18 @@ __device__ __forceinline__ void tc_teardown(TcShared* sh, int* err) {
 #endif
     if (warp == 0) tc::tmem_dealloc(sh->tmem_base, TC_TMEM_COLS);
 }
-__device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int lane) {
+__device__ __forceinline__ void tc_tile_init(TcTile& t, unsigned char* smem, TcShared* sh, int lane, const TcTables* tab_param = nullptr) {
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform by construction
     t.tg = warp >> 3;
     t.smem = smem;
     t.act = smem + t.tg * (TC_NACT * TC_SLOT);
     t.sh = sh;
+#if TC_TAB_PARAM
+    t.tb = tab_param;
+#else
+    (void)tab_param;
     t.tb = reinterpret_cast<const TcTables*>(smem + TC_OFF_TAB);
+#endif
     t.row = 32 * (warp & 3) + lane;
     t.row_off = (uint32_t)((t.row >> 3) * 1024 + (t.row & 7) * 128);
     t.rx = (uint32_t)(t.row & 7);
@@ -809,9 +847,18 @@ __device__ __forceinline__ void tc_load_step_dyn(int st, uint32_t& cc, unsigned 
 
 // MMA issuer warp of tile group TG (whole warp, converged).  TG is a template parameter and every counter derives from
 // kernel parameters and block indices, so that the compiler keeps the whole address arithmetic on the uniform datapath.
+#ifndef TC_ISSUER_SHARED
+#define TC_ISSUER_SHARED 1               // 1: both issuer warps run ONE copy of the (fully unrolled, ~60 KB) issue code
+#endif
+#if TC_ISSUER_SHARED
+__device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int n_pairs) {
+    const int tg = __shfl_sync(0xffffffffu, tg_in, 0);          // warp-uniform: the tile's offsets stay on the uniform datapath
+    const int TG = tg;
+#else
 template <int TG>
 __device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs) {
     constexpr int tg = TG;
+#endif
     const uint32_t act_u32 = tc::smem_u32(tc_smem_raw) + TG * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(tc_smem_raw) + TC_OFF_RING;
     const uint32_t tmem = __shfl_sync(0xffffffffu, sh->tmem_base, 0) + TG * TC_TMEM_TILE;
     const bool lead = tc_elect();
@@ -839,14 +886,22 @@ __device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs)
 #undef ISTEP
 }
 
+#if TC_TAB_PARAM
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant__ TcArgs A, const __grid_constant__ TcTables TAB) {
+#else
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
+#endif
     unsigned char* smem = tc_smem_raw;
     TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = A.V;
     const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
     const int n_pairs = (n_tiles + TC_TILES - 1) / TC_TILES;
+#if TC_TAB_PARAM
+    tc_setup(smem, sh, nullptr, TC_TILES);
+#else
     tc_setup(smem, sh, A.tab, TC_TILES);
+#endif
 
     // Register re-balancing (setmaxnreg, per warpgroup): 20 warps are launched at 96 registers so that the register
     // file of every SM sub-partition (5 warps x 32 x 96 <= 16 K) holds them; the last warpgroup (producer + 3 parked
@@ -854,8 +909,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     if (warp >= TC_TILES * 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
         // ===================================================== weight producer
+#if TC_ISSUER_SHARED
+        if (warp == TC_TILES * 8 + 1 || warp == TC_TILES * 8 + 2) tc_issuer_warp(warp - (TC_TILES * 8 + 1), sh, V, n_pairs);
+#else
         if (warp == TC_TILES * 8 + 1) tc_issuer_warp<0>(sh, V, n_pairs);
         else if (warp == TC_TILES * 8 + 2) tc_issuer_warp<1>(sh, V, n_pairs);
+#endif
         else if (warp == TC_TILES * 8 && lane == 0) {
             uint32_t cc = 0;
 #define LSTEP(ST) tc_load_step<ST>(cc, smem, A.wblob)
@@ -878,7 +937,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
         // ===================================================== tile threads
         TcTile t;
+#if TC_TAB_PARAM
+        tc_tile_init(t, smem, sh, lane, &TAB);
+#else
         tc_tile_init(t, smem, sh, lane);
+#endif
         const int row = t.row, h = t.half, tg = t.tg;
         const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
 
@@ -961,9 +1024,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         const int kp = 8 * s + 2 * j + h;
                         const float4 kc = reinterpret_cast<const float4*>(t.tb->kpt4)[v * NKPT + kp];
                         const float dx = a0.x - kc.x, dy = a0.y - kc.y, dz = a0.z - kc.z;
+#if TC_ABLATE & 2
+                        const float w = (dx * dx + dy * dy + dz * dz) * -72.1347520f;
+                        float s1 = dz, c1 = dx;
+#else
                         const float w = tc_ex2((dx * dx + dy * dy + dz * dz) * -72.1347520f);   // exp(-d^2 / (2 * 0.1^2))
                         float s1, c1;
                         __sincosf(3.14159274f * dz, &s1, &c1);
+#endif
                         const float s2 = 2.0f * s1 * c1, c2 = 1.0f - 2.0f * s1 * s1;
                         const float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
                         t.st_chunk(pslot, 2 * j + h, make_uint4(tc::pack_bf16(dz * w, s1 * w), tc::pack_bf16(c1 * w, s2 * w),

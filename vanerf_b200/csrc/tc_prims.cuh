@@ -44,6 +44,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Returns false when the wait was abandoned (try budget spent, or the abort flag raised by another thread).
 // abort_flag[0] = code of the first wait that gave up, abort_flag[1 + code / 100] = last code of each wait class that
 // was still pending.  No clock and no call: the bound is a try count, so a wait site costs one loop counter.
+// (Measured: pure polling with mbarrier.test_wait instead of the suspending try_wait changes nothing, and moving the
+// retry loop out of line does not pay either.)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
 #pragma unroll 1
     for (int it = 0; it < TC_WAIT_TRIES; ++it) {

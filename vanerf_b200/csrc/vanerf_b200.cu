@@ -46,6 +46,7 @@ struct vanerf_ctx {
     TcTables h_tc;                     // host copy of the biases / small fp32 layers (weights) + camera-space keypoints (frame)
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
+    int tc_waves = 1;
     DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
@@ -117,6 +118,7 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     memset(&c->ft, 0, sizeof(c->ft));
     memset(&c->h_tc, 0, sizeof(c->h_tc));
     memset(&c->h_prog, 0, sizeof(c->h_prog));
+    if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));
 #endif
     *out = c;
     return VANERF_OK;
@@ -393,7 +395,8 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
                  e[0], e[2], e[3], e[4], e[5], e[6]);
         return VANERF_ERR_CUDA;
     }
-    const int max_tiles = TC_TILES * ctx->sm_count;
+    // tiles per launch: `tc_waves` tile pairs per CTA (VANERF_TC_WAVES, default 1 = the chunk's operand images stay in L2)
+    const int max_tiles = TC_TILES * ctx->sm_count * ctx->tc_waves;
     const long long chunk = (long long)max_tiles * TC_ROWS;
     ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
     ENSURE(ctx, ctx->tc_aux, (size_t)max_tiles * TC_ROWS * V * TC_AUX_BYTES);
@@ -406,12 +409,14 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         snprintf(ctx->err, sizeof(ctx->err), "tensor-core path: packing script and compiled MMA program disagree");
         return VANERF_ERR_STATE;
     }
+#if !TC_TAB_PARAM
     if (ctx->tc_tab_dirty) {            // stream-ordered: earlier launches on this stream have read the old tables
         ENSURE(ctx, ctx->tctab, sizeof(TcTables));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tctab.p, &ctx->h_tc, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(stream));          // h_tc may change again before an async copy would read it
         ctx->tc_tab_dirty = false;
     }
+#endif
     for (long long s0 = 0; s0 < N; s0 += chunk) {
         const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
         const int n_tiles = cdiv(nc, TC_ROWS);
@@ -428,7 +433,13 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         a.rec = (const unsigned char*)ctx->tc_rec.p; a.aux = (const unsigned char*)ctx->tc_aux.p;
         a.V = V; a.n_chunk = nc; a.sample0 = s0;
         a.rgba = rgba; a.raw_out = raw_out; a.dbg_latent = dbg_latent; a.err = ctx->tc_err_dev;
+#if TC_TAB_PARAM
+        // the tables (biases, small fp32 layers, camera-space keypoints of the frame) travel by value in the kernel
+        // parameter: constant-bank reads with warp-uniform addresses, no shared memory, no context-global state
+        VANERF_LAUNCH(k_mlp_tc, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
+#else
         VANERF_LAUNCH(k_mlp_tc, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a);
+#endif
         CHECK_LAUNCH(ctx);
     }
     return VANERF_OK;
