@@ -63,6 +63,19 @@
 #endif
 #define TC_SMEM_BYTES (TC_OFF_TRACE + TC_TRACE_N * 8)
 
+#ifndef TC_ROLL_MLP
+#define TC_ROLL_MLP 1                    // the three 128-wide Softplus epilogues of MLPUNet layers1 share one loop body
+#endif
+// Per-view loops of the rendering head: rolled (one copy of each epilogue body, iterations 2.. hit the instruction
+// cache) or unrolled.  Register arrays indexed by the view go through tc_sel3 / tc_set3 so that rolling is legal.
+#ifndef TC_ROLL_VIEWS
+#define TC_ROLL_VIEWS 1
+#endif
+#if TC_ROLL_VIEWS
+#define TC_VLOOP _Pragma("unroll 1")
+#else
+#define TC_VLOOP _Pragma("unroll")
+#endif
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
 #endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating
@@ -203,6 +216,39 @@ constexpr TcProg tc_make_prog() {
     return P;
 }
 constexpr TcProg kProg = tc_make_prog();
+
+// Weight chunks in the order the producer streams them: [geometry + MLP (per view) | density head | texture fusion (per
+// view) | rendering head].  The producer walks this list in a four-instruction loop; an unrolled producer (one code block
+// per chunk) was 60 KB of instructions executed by one lane, which did nothing but evict the tile warps' code from the
+// instruction caches.
+struct TcLoadList {
+    uint32_t src_off[TC_MAX_CHUNKS], bytes[TC_MAX_CHUNKS];
+    int n_gm, n_q, n_t, n_i;
+};
+constexpr TcLoadList tc_make_loads() {
+    TcLoadList L{};
+    const int grp_first[4] = {ST_G1, ST_Q1, ST_T1, ST_I1}, grp_last[4] = {ST_M3, ST_Q3, ST_T4, ST_I9};
+    int n = 0;
+    for (int g = 0; g < 4; ++g) {
+        int cnt = 0;
+        for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
+            if (st == ST_G2) continue;                       // attention layer 2 of GeoVisFusion runs in registers
+            for (int c = 0; c < kProg.steps[st].nchunks; ++c, ++n, ++cnt) {
+                L.src_off[n] = kProg.chunks[kProg.steps[st].chunk0 + c].src_off;
+                L.bytes[n] = kProg.chunks[kProg.steps[st].chunk0 + c].bytes;
+            }
+        }
+        if (g == 0) L.n_gm = cnt;
+        else if (g == 1) L.n_q = cnt;
+        else if (g == 2) L.n_t = cnt;
+        else L.n_i = cnt;
+    }
+    return L;
+}
+constexpr TcLoadList kLoads = tc_make_loads();
+static_assert(kLoads.n_gm == kProg.cc_gm && kLoads.n_q == kProg.cc_q && kLoads.n_t == kProg.cc_t && kLoads.n_i == kProg.cc_i,
+              "producer list and issuer chunk counters disagree");
+__constant__ TcLoadList c_loads = tc_make_loads();
 
 // ================================================================================================ host: script + images
 struct TcOpSpec {
@@ -505,6 +551,10 @@ __device__ __forceinline__ uint32_t tc_mul2(uint32_t a, uint32_t b) {
 }
 __device__ __forceinline__ uint32_t tc_dup_bf16(float g) { return tc::pack_bf16(g, g); }
 
+__device__ __forceinline__ float tc_sel3(const float (&a)[3], int v) { return v == 0 ? a[0] : (v == 1 ? a[1] : a[2]); }
+__device__ __forceinline__ void tc_set3(float (&a)[3], int v, float x) {
+    a[0] = v == 0 ? x : a[0]; a[1] = v == 1 ? x : a[1]; a[2] = v == 2 ? x : a[2];
+}
 __device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
     return tc::mbar_wait(bar, parity, abort_flag, code);
 }
@@ -821,20 +871,6 @@ __device__ __forceinline__ void tc_load_chunk(uint32_t src_off, uint32_t bytes, 
     tc::bulk_g2s(smem + TC_OFF_RING + s * TC_SLOT, wblob + src_off, bytes, &sh->wfull[s]);
     ++cc;
 }
-// weight chunks of step ST (compile-time offsets and sizes)
-template <int ST, int C>
-__device__ __forceinline__ void tc_load_chunks(uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
-    constexpr TcStep S = kProg.steps[ST];
-    if constexpr (C < S.nchunks) {
-        constexpr TcChunk ch = kProg.chunks[S.chunk0 + C];
-        tc_load_chunk(ch.src_off, ch.bytes, cc, smem, wblob, 300 + ST);
-        tc_load_chunks<ST, C + 1>(cc, smem, wblob);
-    }
-}
-template <int ST>
-__device__ __forceinline__ void tc_load_step(uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
-    tc_load_chunks<ST, 0>(cc, smem, wblob);
-}
 // table-driven variant (MMA self test)
 __device__ __forceinline__ void tc_load_step_dyn(int st, uint32_t& cc, unsigned char* smem, const unsigned char* wblob) {
     const TcStep S = c_prog.steps[st];
@@ -917,21 +953,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
         else if (warp == TC_TILES * 8 && lane == 0) {
             uint32_t cc = 0;
-#define LSTEP(ST) tc_load_step<ST>(cc, smem, A.wblob)
 #pragma unroll 1
             for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
                 if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;        // a bounded wait gave up: drain
+                // phases: 0 = geometry + MLP chunks (once per view), 1 = density head, 2 = texture fusion (per view), 3 = head
 #pragma unroll 1
-                for (int v = 0; v < V; ++v) {       // attention layer 2 (ST_G2) runs in registers: no weights to stream
-                    LSTEP(ST_G1); LSTEP(ST_G3); LSTEP(ST_G4); LSTEP(ST_M0); LSTEP(ST_P0); LSTEP(ST_P1); LSTEP(ST_P2); LSTEP(ST_P3);
-                    LSTEP(ST_P4); LSTEP(ST_P5); LSTEP(ST_M1); LSTEP(ST_M2); LSTEP(ST_M3);
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int first = ph == 0 ? 0 : ph == 1 ? kLoads.n_gm : ph == 2 ? kLoads.n_gm + kLoads.n_q : kLoads.n_gm + kLoads.n_q + kLoads.n_t;
+                    const int cnt = ph == 0 ? kLoads.n_gm : ph == 1 ? kLoads.n_q : ph == 2 ? kLoads.n_t : kLoads.n_i;
+                    const int reps = (ph == 0 || ph == 2) ? V : 1;
+#pragma unroll 1
+                    for (int rep = 0; rep < reps; ++rep)
+#pragma unroll 1
+                        for (int i = first; i < first + cnt; ++i)
+                            tc_load_chunk(c_loads.src_off[i], c_loads.bytes[i], cc, smem, A.wblob, 300 + ph);
                 }
-                LSTEP(ST_Q1); LSTEP(ST_Q2); LSTEP(ST_Q3);
-#pragma unroll 1
-                for (int v = 0; v < V; ++v) { LSTEP(ST_T1); LSTEP(ST_T2); LSTEP(ST_T3); LSTEP(ST_T4); }
-                LSTEP(ST_I1); LSTEP(ST_I2); LSTEP(ST_I3); LSTEP(ST_I4); LSTEP(ST_I5); LSTEP(ST_I6); LSTEP(ST_I7); LSTEP(ST_I8); LSTEP(ST_I9);
             }
-#undef LSTEP
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TC_REGS_EPI));
@@ -1047,12 +1084,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 510 + ps);
                     t.pfree_bits ^= 1u << ps;
                 }
+#if TC_ROLL_MLP
+                // h0 -> slots 1, 2; h1 -> slots 4, 0; h2 -> slots 1, 2: one copy of the 64-column Softplus epilogue
+#pragma unroll 1
+                for (int l = 0; l < 3; ++l) {
+                    EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP0 + l) + 64 * h, l == 1 ? (h ? 0 : 4) : 1 + h, 0);
+                    t.step(ST_M1 + l);
+                }
+#else
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP0) + 64 * h, 1 + h, 0);        // h0 -> slots 1, 2
                 t.step(ST_M1);
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP1) + 64 * h, h ? 0 : 4, 0);   // h1 -> slots 4, 0
                 t.step(ST_M2);
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
                 t.step(ST_M3);
+#endif
                 // ---- weighted pooling sums over views in TMEM: S1 += w h3, S2 += w h3^2 (pool_ops, src/utils.py:854-880)
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
@@ -1304,19 +1350,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             // all reads of the f columns precede the accumulator writes of I1 (ordered by the step's publish)
             t.step(ST_I1);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V) tc_epi_store<TA_ELU, 2>(t, 64 * v + 32 * h, BIASP(L_BASE0) + 32 * h, t.slot(2 + v), 4 * h);
             t.step(ST_I2);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
                 if (v < V) {
                     float x[16], y[16];
+                    const float wv = tc_sel3(wt, v);
                     t.ld16(32 * v + 16 * h, x);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_BASE1)[16 * h + i]);
-                        y[i] = x[i] * wt[v];
+                        y[i] = x[i] * wv;
                     }
                     t.st16(160 + 32 * v + 16 * h, x);
                     t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
@@ -1325,11 +1372,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             tc::tmem_st_wait();
             t.step(ST_I3);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS1_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I4);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
                 if (v < V) {
                     float r[16], vv[8], x[16], y[16];
@@ -1349,11 +1396,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             tc::tmem_st_wait();
             t.step(ST_I5);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I6);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
                 if (v < V) {
                     float vv[8], x[16];
@@ -1373,21 +1420,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 }
             }
             t.step(ST_I7);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
             t.step(ST_I8);
-#pragma unroll
+            TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
             t.step(ST_I9);
             if (h == 0) {
-#pragma unroll
+                TC_VLOOP
                 for (int v = 0; v < TC_MAXV; ++v) {
                     if (v < V) {
                         float vv[8];
                         t.ld8(16 * v, vv);
-                        sv[v] = (maskv == 0.0f) ? -1e4f : (vv[0] + BIASP(L_OUT2)[0]);
+                        tc_set3(sv, v, (maskv == 0.0f) ? -1e4f : (vv[0] + BIASP(L_OUT2)[0]));
                     }
                 }
             }
