@@ -142,6 +142,86 @@ def config_dict(args, where):
             "where": where}
 
 
+def run_dynamic(args):
+    """Workload D (BASELINE.json configs[3], render_dynamic): a sequence of frames, each with its own mesh, source images
+    and feature maps and its own 334x512 target camera on a 360-degree path.  A step = `--frames` frames end to end
+    from pinned host buffers: H2D of the frame's maps, per-frame setup (BVH, vertex visibility, vertex tables, bf16 maps),
+    render, D2H of the image.  Frames are dealt round-robin to the ranks (vanerf_b200.dynamic), no collective inside the
+    timed path; per-GPU work shrinks with N ("strong" scaling over a fixed sequence)."""
+    import torch
+    import torch.distributed as dist
+    from vanerf_b200 import dynamic, synthetic, weights
+    from vanerf_b200.model import VANeRF
+
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F = max(args.frames, world)
+    ids = dynamic.frames_for_rank(F, rank, world)
+    net = VANeRF(device=dev, precision=args.precision).eval()
+    net.load_state_dict(weights.init_state_dict(H, W, mode="ref"))
+    pin = lambda t: t.contiguous().pin_memory()
+    frames = {}
+    for f in ids:                                               # synthetic frames of this rank, pinned host memory
+        fr = synthetic.to_torch(synthetic.make_scene(H, W, V, frame=f))
+        fr["img"], fr["feat_tex"] = pin(fr["img"]), pin(fr["feat_tex"])
+        fr["feat_geo"] = [pin(t) for t in fr["feat_geo"]]
+        fr["src_foreground_mask"] = pin(fr["src_foreground_mask"].to(torch.uint8))
+        frames[f] = fr
+    K = frames[ids[0]]["cam_tar"]["K"][0, :3, :3]
+    cams = dynamic.orbit_cameras(F, K, width=W, height=H)
+    out_host = torch.empty(len(ids), 1, 8, H, W).pin_memory()
+
+    def step():
+        dynamic.render_sequence(net, lambda f: frames[f], F, lambda f: [cams[f]], rank, world, out_host=out_host,
+                                fine=True, sample_per_ray_c=S_C, sample_per_ray_f=S_F)
+        torch.cuda.current_stream().synchronize()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = net.renderer.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    sync_all()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        clk = clocks.stop()
+        rps = F * H * W / (ms_step * 1e-3)
+        h2d = dynamic.h2d_bytes(frames[ids[0]]) * F
+        line = {"metric": "rays_per_s", "value": rps, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "ms_per_frame": ms_step / F, "frames_per_s": F / (ms_step * 1e-3), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": f"D: render_dynamic, {F} frames x one 334x512 view (171008 rays, V=3, 64 coarse + 128 fine "
+                                       f"evaluations/ray), per-frame mesh / maps / camera, per-frame setup included",
+                           "precision": args.precision, "frame_partition": "round robin over ranks, no collective in the path",
+                           "l2": "every frame brings new maps and records: the working set exceeds L2", "where": "gpu"},
+                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": F * 8 * H * W * 4,
+                        "note": "the timed step IS the end-to-end path (host buffers in, host images out)"},
+                "gpu_launches": int(net.renderer.launches - l0), "clocks": clk}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -151,11 +231,14 @@ def main():
     # headline = the bf16-MLP tensor-core path (north star kernel 2); the fp32 FFMA path is measured next to it
     ap.add_argument("--precision", default=os.environ.get("VANERF_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-fp32-path", action="store_true", help="skip the secondary fp32-path measurement")
-    ap.add_argument("--workload", default="B", choices=["B", "C"])
+    ap.add_argument("--workload", default="B", choices=["B", "C", "D"])
+    ap.add_argument("--frames", type=int, default=8, help="workload D: frames per step (BASELINE.json configs[3] uses 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "D":
+        return run_dynamic(args)
 
     import torch
     import torch.distributed as dist

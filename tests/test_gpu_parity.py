@@ -113,3 +113,37 @@ def test_cuda_errors_are_loud(cuda_lib):
     r = Renderer("cuda:0")
     with pytest.raises(L.VanerfError):
         r.lib.check(r.ctx, r.lib.dll.vanerf_geom_query(r.ctx, None, None, None, 1, 1, None, None, None, None, None, None), "geom")
+
+
+def test_cuda_render_sequence_frames_are_independent(cuda_lib):
+    """render_dynamic driver (vanerf_b200.dynamic, BASELINE.json configs[3]): every frame of a sequence rendered through
+    one network object equals that frame rendered alone, whatever came before it; the round-robin rank shards cover
+    the sequence (the ranks of a 2-GPU job, run here one after the other on cuda:0)."""
+    from vanerf_b200 import dynamic, synthetic, weights
+    from vanerf_b200.model import VANeRF
+    H, W, V, F = 256, 256, 3, 3
+    sd = weights.init_state_dict(H, W, mode="stress")
+    frames = {f: synthetic.to_torch(synthetic.make_scene(H, W, V, frame=f)) for f in range(F)}
+    K = frames[0]["cam_tar"]["K"][0, :3, :3]
+    cams = dynamic.orbit_cameras(F, K, width=W, height=H)
+    cfg = dict(fine=True, sample_per_ray_c=16, sample_per_ray_f=16)
+
+    def make_net():
+        n = VANeRF(device=torch.device("cuda:0"), precision="fp32").eval()
+        n.load_state_dict(sd)
+        return n
+
+    net = make_net()
+    ids, seq = dynamic.render_sequence(net, lambda f: frames[f], F, lambda f: [cams[f]], 0, 1, **cfg)
+    assert ids == list(range(F))
+    for f in range(F):
+        alone = dynamic.render_novel_views(make_net(), dynamic.to_device_frame(frames[f], "cuda:0"), [cams[f]], **cfg)
+        assert torch.equal(seq[f], alone), f"frame {f} depends on its predecessors"
+        assert torch.isfinite(seq[f]).all()
+    assert not torch.equal(seq[0], seq[1])
+    # the two shards of a 2-rank job
+    got = {}
+    for rank in range(2):
+        ids_r, out_r = dynamic.render_sequence(make_net(), lambda f: frames[f], F, lambda f: [cams[f]], rank, 2, **cfg)
+        got.update(dict(zip(ids_r, out_r)))
+    assert sorted(got) == list(range(F)) and all(torch.equal(got[f], seq[f]) for f in range(F))

@@ -81,7 +81,9 @@ inline void build_triangles(const float* verts, const int32_t* faces, int n_face
             boxes[f].mx[c] = std::max(a, std::max(b, d));
         }
     }
-    build(boxes, 4, out);          // leaf sizes from a sweep on B200 (2/4/8 triangles x 4/8/16 vertices)
+    // leaf sizes from sweeps on B200 (2/4/8/16 triangles with the per-triangle lower bound x 4/8/16 vertices); VANERF_TRI_LEAF: developer override
+    const char* e = std::getenv("VANERF_TRI_LEAF");
+    build(boxes, e ? std::max(1, std::min(32, std::atoi(e))) : 8, out);
 }
 
 inline void build_points(const float* pts, int n, Tree& out) {

@@ -21,6 +21,7 @@
 
 #define MAXV VANERF_MAX_VIEWS
 #define NKPT VANERF_N_KPT
+#define TRI_REC_F4 6             // float4 per triangle record (geom.cuh)
 #define NUM_V_HAND 779          // src/networks.py:25  (twin vertex = (id + 779) mod 1558)
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -101,7 +102,7 @@ struct FrameDev {                 // filled by vanerf_frame_setup, passed by val
     // per-primitive records in leaf order, so that a leaf visit is one dependent load instead of prims -> faces -> verts:
     // triangle = 4 x float4 {a.xyz, as_float(face id)}, {b.xyz, ab.x}, {c.xyz, ab.y}, {ab.z, ac.xyz} with ab = b - a,
     // ac = c - a rounded exactly as the kernels' xsub does; vertex = {xyz, as_float(vertex id)}
-    const float4* tri_rec;
+    const float4* tri_rec;      // TRI_REC_F4 float4 per triangle, leaf order: a|id, b|ab.x, c|ab.y, ab.z|ac, n|r, centre
     const float4* vtx_rec;
 };
 

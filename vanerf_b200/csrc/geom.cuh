@@ -8,6 +8,9 @@
 #include "rays.cuh"
 
 #define BVH_STACK 48
+#ifndef GEOM_TRI_LB
+#define GEOM_TRI_LB 1        // per-triangle lower bound (plane distance + bounding circle) before the exact distance
+#endif
 
 // ab = b - a and ac = c - a are passed in (precomputed per frame with the same rounding as xsub)
 __device__ __forceinline__ float point_tri_dist2(const float* p, const float* a, const float* b, const float* c,
@@ -91,19 +94,35 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
-                const float4* rec = fr.tri_rec + 4 * (first + i);
-                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+                const float4* rec = fr.tri_rec + TRI_REC_F4 * (first + i);
+#if GEOM_TRI_LB
+                {   // Lower bound of the distance to the triangle: it lies in its plane (unit normal n, through c) inside
+                    // the circle (c, r), so dist^2 >= h^2 + max(0, sqrt(|p - c|^2 - h^2) - r)^2 with h = n . (p - c).
+                    // An AABB bound lets every triangle within ~sqrt(2 D e) of the foot point through (D = distance,
+                    // e = edge length: ~60 exact tests per far sample); this one passes the few whose circle covers it.
+                    // Only a prune (r is inflated on the host, slack 1e-4 relative): the result stays the exact first minimum.
+                    const float4 l0 = rec[4], l1 = rec[5];
+                    const float ex = p[0] - l1.x, ey = p[1] - l1.y, ez = p[2] - l1.z;
+                    const float h = l0.x * ex + l0.y * ey + l0.z * ez;
+                    const float e2 = ex * ex + ey * ey + ez * ez;
+                    const float s = fmaxf(sqrtf(fmaxf(e2 - h * h, 0.0f)) - l0.w, 0.0f);
+                    if (h * h + s * s > best_d * 1.0001f + 1e-10f) continue;
+                }
+#endif
+                const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+                const float4 r3 = rec[3];
                 const int f = __float_as_int(r0.w);
                 const float va[3] = {r0.x, r0.y, r0.z}, vb[3] = {r1.x, r1.y, r1.z}, vc[3] = {r2.x, r2.y, r2.z};
                 const float d = point_tri_dist2(p, va, vb, vc, r1.w, r2.w, r3.x, r3.y, r3.z, r3.w);
                 if (d < best_d || (d == best_d && f < best_f)) { best_d = d; best_f = f; }
             }
         } else {
-            // near child last (popped first)
+            // near child last (popped first); a child that cannot beat the current best is not pushed at all
             const float da = aabb_dist2(fr.tri_nodes[2 * a], fr.tri_nodes[2 * a + 1], p);
             const float db = aabb_dist2(fr.tri_nodes[2 * b], fr.tri_nodes[2 * b + 1], p);
-            if (da < db) { stack[sp++] = b; stack[sp++] = a; }
-            else { stack[sp++] = a; stack[sp++] = b; }
+            const float thr = best_d * 1.00001f + 1e-12f;
+            if (da < db) { if (db <= thr) stack[sp++] = b; if (da <= thr) stack[sp++] = a; }
+            else { if (da <= thr) stack[sp++] = a; if (db <= thr) stack[sp++] = b; }
         }
     }
 }
@@ -123,7 +142,7 @@ __device__ __forceinline__ bool inside_parity(const FrameDev& fr, const float* p
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
-                const float4* rec = fr.tri_rec + 4 * (first + i);
+                const float4* rec = fr.tri_rec + TRI_REC_F4 * (first + i);
                 const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
                 const float v0[3] = {r0.x, r0.y, r0.z};
                 const float e10 = r1.w, e11 = r2.w, e12 = r3.x;        // v1 - v0
@@ -207,7 +226,10 @@ __device__ __forceinline__ void bary_of_projection(const FrameDev& fr, const flo
 
 // One thread per sample.  Outputs may be NULL.
 // pts_in != NULL: explicit query points (VANeRF.query called directly) instead of cam_pos + dir * z.
-__global__ void k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
+#ifndef GEOM_MINB
+#define GEOM_MINB 12       // 40 registers: 48 warps per SM hide the dependent node loads (sweep: 8 -> 36.7 ms, 12 -> 36.0, 16 -> 43.3)
+#endif
+__global__ void __launch_bounds__(128, GEOM_MINB) k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
                              const float* __restrict__ pts_in, int R, int S, float* __restrict__ pts, float* __restrict__ sdf,
                              int* __restrict__ face, int* __restrict__ nn_vert, unsigned char* __restrict__ qvis) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,12 +243,18 @@ __global__ void k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict
     // nearest vertex first: its squared distance bounds the closest-face distance from above (the vertex belongs to a
     // face), which prunes most of the triangle traversal.  Inflated by 1e-4 relative so that rounding differences
     // between the two distance formulas (~1e-6) cannot exclude the true closest face.
-    float dnn2;
-    const int nnv = nearest_vertex(fr, p, dnn2);
-    float d2; int f;
-    closest_face(fr, p, dnn2 * 1.0001f + 1e-12f, d2, f);
-    if (f == 0x7fffffff) closest_face(fr, p, __int_as_float(0x7f800000), d2, f);     // never expected; keeps the result exact
-    const bool in = inside_parity(fr, p);
+#ifndef GEOM_ABLATE
+#define GEOM_ABLATE 0        // developer timing experiments (wrong results): 1 no nearest vertex, 2 no closest face, 4 no parity
+#endif
+    float dnn2 = 1e-4f;
+    int nnv = 0;
+    if (!(GEOM_ABLATE & 1)) nnv = nearest_vertex(fr, p, dnn2);
+    float d2 = 1e-4f; int f = 0;
+    if (!(GEOM_ABLATE & 2)) {
+        closest_face(fr, p, dnn2 * 1.0001f + 1e-12f, d2, f);
+        if (f == 0x7fffffff) closest_face(fr, p, __int_as_float(0x7f800000), d2, f);     // never expected; keeps the result exact
+    }
+    const bool in = (GEOM_ABLATE & 4) ? false : inside_parity(fr, p);
     // pts_sdf = sqrt(d2 + 1e-6) * (-2 * (inside - 0.5))   (mesh_util.py:510-512)
     const float dist = xsqrt(xadd(d2, 1e-6f));
     const float sign = xmul(-2.0f, xsub(in ? 1.0f : 0.0f, 0.5f));

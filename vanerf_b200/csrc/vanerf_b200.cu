@@ -250,7 +250,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     bvh::build_points(f->verts, Nv, vt);
 
     // per-primitive records in leaf order (see FrameDev); b - a and c - a are rounded once, exactly like xsub
-    std::vector<float> trec((size_t)tt.prims.size() * 16), vrec((size_t)vt.prims.size() * 4);
+    std::vector<float> trec((size_t)tt.prims.size() * 4 * TRI_REC_F4), vrec((size_t)vt.prims.size() * 4);
     for (size_t i = 0; i < tt.prims.size(); ++i) {
         const int fi = tt.prims[i];
         const float* a = f->verts + 3 * f->faces[3 * fi];
@@ -258,7 +258,25 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
         const float* c = f->verts + 3 * f->faces[3 * fi + 2];
         volatile float ab[3], ac[3];
         for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
-        float* r = &trec[16 * i];
+        float* r = &trec[4 * TRI_REC_F4 * i];
+        {   // lower-bound record: unit normal, centroid, radius of the circle around it (inflated: the bound must never
+            // exceed the true distance despite rounding); a degenerate triangle gets n = 0 (sphere bound)
+            double n[3] = {(double)ab[1] * ac[2] - (double)ab[2] * ac[1], (double)ab[2] * ac[0] - (double)ab[0] * ac[2],
+                           (double)ab[0] * ac[1] - (double)ab[1] * ac[0]};
+            const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            double cen[3], rad = 0.0;
+            for (int k = 0; k < 3; ++k) cen[k] = ((double)a[k] + b[k] + c[k]) / 3.0;
+            const float* vs[3] = {a, b, c};
+            for (int q = 0; q < 3; ++q) {
+                double d2 = 0.0;
+                for (int k = 0; k < 3; ++k) d2 += (vs[q][k] - (float)cen[k]) * (double)(vs[q][k] - (float)cen[k]);
+                rad = std::max(rad, sqrt(d2));
+            }
+            for (int k = 0; k < 3; ++k) r[16 + k] = nl > 1e-20 ? (float)(n[k] / nl) : 0.0f;
+            r[19] = (float)(rad * 1.0001 + 1e-7);
+            for (int k = 0; k < 3; ++k) r[20 + k] = (float)cen[k];
+            r[23] = 0.0f;
+        }
         r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = bvh::as_float(fi);
         r[4] = b[0]; r[5] = b[1]; r[6] = b[2]; r[7] = ab[0];
         r[8] = c[0]; r[9] = c[1]; r[10] = c[2]; r[11] = ab[1];
