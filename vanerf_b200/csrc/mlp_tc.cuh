@@ -884,6 +884,10 @@ __device__ __forceinline__ void tc_load_step_dyn(int st, uint32_t& cc, unsigned 
     }
 }
 
+// (Measured and dropped: a table-driven issuer - a ~100-instruction loop over a constant op table, records fetched one op
+// ahead, K steps issued as one burst - instead of the ~55 KB of unrolled issue code below: 97.7 vs 92.3 ms per view.  The
+// issue latency between "operands ready" and the last MMA of a step is on every tile's critical path, and immediates beat
+// table lookups there even though the unrolled code is cold.)
 // MMA issuer warp of tile group TG (whole warp, converged).  TG is a template parameter and every counter derives from
 // kernel parameters and block indices, so that the compiler keeps the whole address arithmetic on the uniform datapath.
 #ifndef TC_ISSUER_SHARED
