@@ -10,6 +10,7 @@
 // Masks / `valid` keep the exact-op contract (bit-exact vs the oracle); features are rounded to bf16 once.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdio>
 #include "common.cuh"
 #include "gather.cuh"
 #include "tc_prims.cuh"
@@ -84,12 +85,62 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             long long N_total, const float* __restrict__ sdf, const int* __restrict__ nn_vert,
             const unsigned char* __restrict__ qvis, unsigned char* __restrict__ rec, unsigned char* __restrict__ aux,
             unsigned char* __restrict__ valid_out) {
-    const int lane = threadIdx.x & 7;
-    const int group = (blockIdx.x * GTC_THREADS + threadIdx.x) >> 3;
-    const int n_groups = (gridDim.x * GTC_THREADS) >> 3;
+    // A warp handles 8 samples per iteration.  Pass 1 (per (sample, view): projection, masks, boundary weight, image and
+    // foreground taps, the tap set of the 64-channel map; exact-op sequences) runs on lane = 4 * sample + view, i.e. on 24
+    // of 32 lanes at V = 3 (it used to run on 3 lanes of each 8-lane sample group: 12 of 32).  Pass 2 (the wide copies,
+    // 8 lanes x 16 bytes per sample) takes the 8 samples in two rounds of four and reads pass 1 by shuffle.
+    const int lane32 = threadIdx.x & 31;
+    const int lane = lane32 & 7;
+    const int warp_g = (blockIdx.x * GTC_THREADS + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * GTC_THREADS) >> 5;
     const int V = fr.V;
-    const int n_rows = ((n_chunk + TC_ROWS - 1) / TC_ROWS) * TC_ROWS;
-    for (int i = group; i < n_rows; i += n_groups) {
+    const int n_rows = ((n_chunk + TC_ROWS - 1) / TC_ROWS) * TC_ROWS;          // multiple of 8
+    for (int i8 = warp_g * 8; i8 < n_rows; i8 += n_warps * 8) {
+        // ---- pass 1
+        float mx = 0.f, my = 0.f, mw = 0.f, mcr = 0.f, mcg = 0.f, mcb = 0.f;
+        int mok = 1;
+        Bilin mb;
+        mb.i00 = mb.i01 = mb.i10 = mb.i11 = 0; mb.nw = mb.ne = mb.sw = mb.se = 0.f;
+        {
+            const int i1 = i8 + (lane32 >> 2), v = lane32 & 3;
+            const long long n1 = sample0 + (i1 < n_chunk ? i1 : n_chunk - 1);
+            if (v < V) {
+                float p[3];
+                if (pts_in) { p[0] = pts_in[3 * n1]; p[1] = pts_in[3 * n1 + 1]; p[2] = pts_in[3 * n1 + 2]; }
+                else sample_point(rays + (size_t)(n1 / S) * VANERF_RAY_STRIDE, tar.cam_pos, z[n1], p);
+                const ViewProj q = project_sample(fr, v, p);
+                const Bilin b = bilin_setup(q.x, q.y, fr.W, fr.H);
+                // the image tap (r, g, b) reads the same four texels as the foreground-mask tap: do both here
+                const float4* ip = reinterpret_cast<const float4*>(fr.imgm) + (size_t)v * fr.H * fr.W;
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef GTC_DEBUG
+                if (b.i00 < 0 || b.i00 >= fr.H * fr.W || b.i01 >= fr.H * fr.W || b.i10 >= fr.H * fr.W || b.i11 >= fr.H * fr.W || n1 < 0 || n1 >= N_total)
+                    printf("GTC_DEBUG pass1 blk %d thr %d i1 %d n1 %lld v %d idx %d %d %d %d\n", blockIdx.x, threadIdx.x, i1, n1, v, b.i00, b.i01, b.i10, b.i11);
+#endif
+                const float4 t00 = ip[b.i00], t01 = b.i01 >= 0 ? ip[b.i01] : z4, t10 = b.i10 >= 0 ? ip[b.i10] : z4, t11 = b.i11 >= 0 ? ip[b.i11] : z4;
+                const float fgv = bilin_mix(b, t00.w, t01.w, t10.w, t11.w);
+                mcr = bilin_mix(b, t00.x, t01.x, t10.x, t11.x);
+                mcg = bilin_mix(b, t00.y, t01.y, t10.y, t11.y);
+                mcb = bilin_mix(b, t00.z, t01.z, t10.z, t11.z);
+                mok = (q.in && fgv > 0.1f) ? 1 : 0;
+                float w = 1.0f;
+                const float q3[3] = {q.x, q.y, q.zn};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float qq = 0.5f * q3[c] + 0.5f;
+                    const float d = fminf(qq, 1.0f - qq);
+                    w *= sigmoidf_(5.0f * (d / 0.1f - 1.0f));
+                }
+                mx = q.x; my = q.y; mw = w;
+                mb = bilin_setup(q.x, q.y, fr.g0w, fr.g0h);
+            }
+        }
+        // ---- pass 2, four samples per round
+#pragma unroll 1
+        for (int rnd = 0; rnd < 2; ++rnd) {
+        const int s8 = 4 * rnd + (lane32 >> 3);                 // sample of this 8-lane group within the warp's eight
+        const int src0 = 4 * s8;                                // pass-1 lane of (sample, view 0)
+        const int i = i8 + s8;
         const bool real = i < n_chunk;
         const long long n = sample0 + (real ? i : n_chunk - 1);
         float p[3];
@@ -101,44 +152,14 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
             ray = rays + (size_t)(n / S) * VANERF_RAY_STRIDE;
             sample_point(ray, tar.cam_pos, z[n], p);
         }
-        // ---- pass 1, one lane per view (lane v < V of the sample's 8 lanes; the same exact-op sequence as before,
-        // just not repeated by all 8 lanes): projection, in-frustum and foreground masks, boundary weight, and the
-        // bilinear tap set of the 64-channel map; the results are shared with 8-wide shuffles.
-        float mx = 0.f, my = 0.f, mw = 0.f, mcr = 0.f, mcg = 0.f, mcb = 0.f;
-        int mok = 1;
-        Bilin mb;
-        mb.i00 = mb.i01 = mb.i10 = mb.i11 = 0; mb.nw = mb.ne = mb.sw = mb.se = 0.f;
-        if (lane < V) {
-            const int v = lane;
-            const ViewProj q = project_sample(fr, v, p);
-            const Bilin b = bilin_setup(q.x, q.y, fr.W, fr.H);
-            // the image tap (r, g, b) reads the same four texels as the foreground-mask tap: do both here
-            const float4* ip = reinterpret_cast<const float4*>(fr.imgm) + (size_t)v * fr.H * fr.W;
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 t00 = ip[b.i00], t01 = b.i01 >= 0 ? ip[b.i01] : z4, t10 = b.i10 >= 0 ? ip[b.i10] : z4, t11 = b.i11 >= 0 ? ip[b.i11] : z4;
-            const float fgv = bilin_mix(b, t00.w, t01.w, t10.w, t11.w);
-            mcr = bilin_mix(b, t00.x, t01.x, t10.x, t11.x);
-            mcg = bilin_mix(b, t00.y, t01.y, t10.y, t11.y);
-            mcb = bilin_mix(b, t00.z, t01.z, t10.z, t11.z);
-            mok = (q.in && fgv > 0.1f) ? 1 : 0;
-            float w = 1.0f;
-            const float q3[3] = {q.x, q.y, q.zn};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float qq = 0.5f * q3[c] + 0.5f;
-                const float d = fminf(qq, 1.0f - qq);
-                w *= sigmoidf_(5.0f * (d / 0.1f - 1.0f));
-            }
-            mx = q.x; my = q.y; mw = w;
-            mb = bilin_setup(q.x, q.y, fr.g0w, fr.g0h);
-        }
         float pw[MAXV];
         bool m = true;
 #pragma unroll
         for (int v = 0; v < MAXV; ++v) {
             if (v < V) {
-                pw[v] = __shfl_sync(0xffffffffu, mw, v, 8);
-                m = m && (__shfl_sync(0xffffffffu, mok, v, 8) != 0);
+                pw[v] = __shfl_sync(0xffffffffu, mw, src0 + v);
+                const int okv = __shfl_sync(0xffffffffu, mok, src0 + v);       // unconditionally: `m && shfl(...)` would let
+                m = m && (okv != 0);                                            // lanes with m == false skip a warp-wide shuffle
             }
         }
         const float mf = m ? 1.0f : 0.0f;
@@ -160,15 +181,26 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
         for (int v = 0; v < MAXV; ++v) {
             if (v >= V) break;
             unsigned char* img = rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
-            const float x = __shfl_sync(0xffffffffu, mx, v, 8), y = __shfl_sync(0xffffffffu, my, v, 8);
-            const float cr = __shfl_sync(0xffffffffu, mcr, v, 8), cg = __shfl_sync(0xffffffffu, mcg, v, 8), cb = __shfl_sync(0xffffffffu, mcb, v, 8);
+            const float x = __shfl_sync(0xffffffffu, mx, src0 + v), y = __shfl_sync(0xffffffffu, my, src0 + v);
+            const float cr = __shfl_sync(0xffffffffu, mcr, src0 + v), cg = __shfl_sync(0xffffffffu, mcg, src0 + v), cb = __shfl_sync(0xffffffffu, mcb, src0 + v);
             Bilin b64;
-            b64.i00 = __shfl_sync(0xffffffffu, mb.i00, v, 8); b64.i01 = __shfl_sync(0xffffffffu, mb.i01, v, 8);
-            b64.i10 = __shfl_sync(0xffffffffu, mb.i10, v, 8); b64.i11 = __shfl_sync(0xffffffffu, mb.i11, v, 8);
-            b64.nw = __shfl_sync(0xffffffffu, mb.nw, v, 8); b64.ne = __shfl_sync(0xffffffffu, mb.ne, v, 8);
-            b64.sw = __shfl_sync(0xffffffffu, mb.sw, v, 8); b64.se = __shfl_sync(0xffffffffu, mb.se, v, 8);
+            b64.i00 = __shfl_sync(0xffffffffu, mb.i00, src0 + v); b64.i01 = __shfl_sync(0xffffffffu, mb.i01, src0 + v);
+            b64.i10 = __shfl_sync(0xffffffffu, mb.i10, src0 + v); b64.i11 = __shfl_sync(0xffffffffu, mb.i11, src0 + v);
+            b64.nw = __shfl_sync(0xffffffffu, mb.nw, src0 + v); b64.ne = __shfl_sync(0xffffffffu, mb.ne, src0 + v);
+            b64.sw = __shfl_sync(0xffffffffu, mb.sw, src0 + v); b64.se = __shfl_sync(0xffffffffu, mb.se, src0 + v);
             const size_t vb = (size_t)v * fr.n_verts;
             const float qv = qvis[(size_t)v * N_total + n] ? 1.0f : 0.0f, vn = fr.vis[vb + nn], vt = fr.vis[vb + tw];
+#ifdef GTC_DEBUG
+            {
+                const int lim = fr.g0h * fr.g0w;
+                if (b64.i00 < 0 || b64.i00 >= lim || b64.i01 >= lim || b64.i10 >= lim || b64.i11 >= lim || nn < 0 || nn >= fr.n_verts ||
+                    tw < 0 || tw >= fr.n_verts || n < 0 || n >= N_total || tile < 0) {
+                    printf("GTC_DEBUG blk %d thr %d i %d n %lld v %d src0 %d idx %d %d %d %d lim %d nn %d tw %d\n", blockIdx.x, threadIdx.x, i, n, v, src0,
+                           b64.i00, b64.i01, b64.i10, b64.i11, lim, nn, tw);
+                    continue;
+                }
+            }
+#endif
             // R0: pixel-aligned geo0, R1 / R2: nearest / twin vertex rows (already multiplied by visibility)
             *reinterpret_cast<uint4*>(img + off) = tap8_bf16(ft.geo0 + (size_t)v * fr.g0h * fr.g0w * 64, 64, 8 * lane, b64);
             *reinterpret_cast<uint4*>(img + TC_SLOT + off) = *reinterpret_cast<const uint4*>(ft.T64 + (vb + nn) * 64 + 8 * lane);
@@ -249,5 +281,6 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
                 *reinterpret_cast<uint4*>(aux + ((size_t)i * V + v) * TC_AUX_BYTES + 16 * lane) = o;
             }
         }
+        }   // round
     }
 }

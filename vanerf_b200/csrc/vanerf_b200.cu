@@ -440,7 +440,7 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         const int n_tiles = cdiv(nc, TC_ROWS);
         {
             TimedScope ts(ctx, KCL_GATHER, stream);
-            const int gblocks = min(cdiv((long long)n_tiles * TC_ROWS, GTC_THREADS / 8), ctx->sm_count * 8);
+            const int gblocks = min(cdiv((long long)n_tiles * TC_ROWS, GTC_THREADS / 4), ctx->sm_count * 8);      // 8 samples per warp and iteration
             VANERF_LAUNCH(k_gather_tc, gblocks, GTC_THREADS, 0, stream, ctx->fr, ctx->ft, td, rays, z, pts_in, view_in, S, s0, nc, N,
                           sdf, nn, qvis, (unsigned char*)ctx->tc_rec.p, (unsigned char*)ctx->tc_aux.p, valid);
             CHECK_LAUNCH(ctx);
