@@ -3,6 +3,7 @@
 // leaf: a = ~first_prim (negative), b = prim count.  Prims are indices into the original arrays, in leaf order.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,62 @@ inline void build_triangles(const float* verts, const int32_t* faces, int n_face
     // leaf sizes from sweeps on B200 (2/4/8/16 triangles with the per-triangle lower bound x 4/8/16 vertices); VANERF_TRI_LEAF: developer override
     const char* e = std::getenv("VANERF_TRI_LEAF");
     build(boxes, e ? std::max(1, std::min(32, std::atoi(e))) : 8, out);
+}
+
+// Per-node slab bound for the closest-triangle search (geom.cuh): every point of the node's triangles lies within
+// |n . (x - c)| <= t of the plane (unit n, through c) and, projected into it, within r of c.  8 floats per node:
+// n.xyz, t | c.xyz, r (t and r inflated so that rounding can only loosen the bound).  The direction is whichever of
+// {area-weighted normal of the node's triangles, x, y, z} gives the thinnest slab.
+inline void triangle_node_bounds(const Tree& t, const float* verts, const int32_t* faces, std::vector<float>& lb) {
+    const int nn = t.n_nodes();
+    lb.assign((size_t)nn * 8, 0.0f);
+    std::vector<int> first(nn), count(nn);
+    auto as_int = [](float f) { int v; std::memcpy(&v, &f, 4); return v; };
+    for (int i = nn - 1; i >= 0; --i) {                      // children have larger indices than their parent
+        const int a = as_int(t.nodes[8 * (size_t)i + 3]), b = as_int(t.nodes[8 * (size_t)i + 7]);
+        if (a < 0) { first[i] = ~a; count[i] = b; }
+        else { first[i] = std::min(first[a], first[b]); count[i] = count[a] + count[b]; }
+    }
+    std::vector<double> pts;
+    for (int i = 0; i < nn; ++i) {
+        pts.clear();
+        double an[3] = {0, 0, 0}, c[3] = {0, 0, 0};
+        for (int k = first[i]; k < first[i] + count[i]; ++k) {
+            const int f = t.prims[k];
+            const float* v0 = verts + 3 * faces[3 * f];
+            const float* v1 = verts + 3 * faces[3 * f + 1];
+            const float* v2 = verts + 3 * faces[3 * f + 2];
+            const double u[3] = {(double)v1[0] - v0[0], (double)v1[1] - v0[1], (double)v1[2] - v0[2]};
+            const double w[3] = {(double)v2[0] - v0[0], (double)v2[1] - v0[1], (double)v2[2] - v0[2]};
+            an[0] += u[1] * w[2] - u[2] * w[1]; an[1] += u[2] * w[0] - u[0] * w[2]; an[2] += u[0] * w[1] - u[1] * w[0];
+            for (const float* v : {v0, v1, v2}) { pts.push_back(v[0]); pts.push_back(v[1]); pts.push_back(v[2]); c[0] += v[0]; c[1] += v[1]; c[2] += v[2]; }
+        }
+        const size_t np = pts.size() / 3;
+        float cf[3];
+        for (int k = 0; k < 3; ++k) cf[k] = (float)(c[k] / (double)np);
+        double cand[4][3] = {{an[0], an[1], an[2]}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        double best_t = 1e300, best_r = 0.0;
+        float best_n[3] = {0, 0, 0};
+        for (int q = 0; q < 4; ++q) {
+            const double nl = std::sqrt(cand[q][0] * cand[q][0] + cand[q][1] * cand[q][1] + cand[q][2] * cand[q][2]);
+            if (nl < 1e-30) continue;
+            float nf[3];
+            for (int k = 0; k < 3; ++k) nf[k] = (float)(cand[q][k] / nl);
+            const double nfl = std::sqrt((double)nf[0] * nf[0] + (double)nf[1] * nf[1] + (double)nf[2] * nf[2]);   // ~1: the stored vector
+            double tt = 0.0, rr = 0.0;
+            for (size_t j = 0; j < np; ++j) {
+                const double e[3] = {pts[3 * j] - cf[0], pts[3 * j + 1] - cf[1], pts[3 * j + 2] - cf[2]};
+                const double h = (nf[0] * e[0] + nf[1] * e[1] + nf[2] * e[2]) / nfl;
+                const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+                tt = std::max(tt, std::fabs(h));
+                rr = std::max(rr, std::sqrt(std::max(e2 - h * h, 0.0)));
+            }
+            if (tt < best_t) { best_t = tt; best_r = rr; for (int k = 0; k < 3; ++k) best_n[k] = nf[k]; }
+        }
+        float* o = &lb[8 * (size_t)i];
+        o[0] = best_n[0]; o[1] = best_n[1]; o[2] = best_n[2]; o[3] = (float)(best_t * 1.001 + 1e-6);
+        o[4] = cf[0]; o[5] = cf[1]; o[6] = cf[2]; o[7] = (float)(best_r * 1.001 + 1e-6);
+    }
 }
 
 inline void build_points(const float* pts, int n, Tree& out) {

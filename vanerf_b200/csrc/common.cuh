@@ -98,6 +98,7 @@ struct FrameDev {                 // filled by vanerf_frame_setup, passed by val
     const float* verts;                    // (Nv,3)
     const int* faces;                      // (F,3)
     const float4* tri_nodes; const int* tri_prims;   // BVH over triangles (prims = face ids in leaf order)
+    const float4* tri_node_lb;                       // per node: slab bound n.xyz, t | c.xyz, r (bvh::triangle_node_bounds)
     const float4* vtx_nodes; const int* vtx_prims;   // BVH over vertices
     // per-primitive records in leaf order, so that a leaf visit is one dependent load instead of prims -> faces -> verts:
     // triangle = 4 x float4 {a.xyz, as_float(face id)}, {b.xyz, ab.x}, {c.xyz, ab.y}, {ab.z, ac.xyz} with ab = b - a,

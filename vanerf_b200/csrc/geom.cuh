@@ -8,6 +8,9 @@
 #include "rays.cuh"
 
 #define BVH_STACK 48
+#ifndef GEOM_NODE_LB
+#define GEOM_NODE_LB 1       // per-node slab bound (plane + thickness + bounding circle) after the box test
+#endif
 #ifndef GEOM_TRI_LB
 #define GEOM_TRI_LB 1        // per-triangle lower bound (plane distance + bounding circle) before the exact distance
 #endif
@@ -90,6 +93,17 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
         const int ni = stack[--sp];
         const float4 mn = fr.tri_nodes[2 * ni], mx = fr.tri_nodes[2 * ni + 1];
         if (aabb_dist2(mn, mx, p) > best_d * 1.00001f + 1e-12f) continue;
+#if GEOM_NODE_LB
+        {   // slab bound of the node (bvh::triangle_node_bounds): for a smooth patch far from p it is much tighter than the
+            // box, whose slack lets every node within ~sqrt(2 D size) of the foot point through
+            const float4 l0 = fr.tri_node_lb[2 * ni], l1 = fr.tri_node_lb[2 * ni + 1];
+            const float ex = p[0] - l1.x, ey = p[1] - l1.y, ez = p[2] - l1.z;
+            const float h = l0.x * ex + l0.y * ey + l0.z * ez;
+            const float e2 = ex * ex + ey * ey + ez * ez;
+            const float u = fmaxf(fabsf(h) - l0.w, 0.0f), s = fmaxf(sqrtf(fmaxf(e2 - h * h, 0.0f)) - l1.w, 0.0f);
+            if (u * u + s * s > best_d * 1.0001f + 1e-10f) continue;
+        }
+#endif
         const int a = __float_as_int(mn.w), b = __float_as_int(mx.w);
         if (a < 0) {
             const int first = ~a;

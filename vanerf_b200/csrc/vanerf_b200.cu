@@ -58,7 +58,7 @@ struct vanerf_ctx {
     FrameDev fr;
     bool have_frame = false;
     DevBuf geo0, geo1, tex, imgm, T64, T8, Ttex, vis, verts, faces, tri_nodes, tri_prims, vtx_nodes, vtx_prims,
-        kpt_cam, xyz_ndc, xy11, zbuf, tri_rec, vtx_rec;
+        kpt_cam, xyz_ndc, xy11, zbuf, tri_rec, vtx_rec, tri_node_lb;
     // scratch
     DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
 };
@@ -133,7 +133,7 @@ void vanerf_ctx_destroy(vanerf_ctx* c) {
 #endif
     DevBuf* all[] = {&c->wblob, &c->netdev, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
                      &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
-                     &c->xyz_ndc, &c->xy11, &c->zbuf, &c->tri_rec, &c->vtx_rec, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
+                     &c->xyz_ndc, &c->xy11, &c->zbuf, &c->tri_rec, &c->vtx_rec, &c->tri_node_lb, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
                      &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     delete c;
@@ -248,6 +248,8 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     bvh::Tree tt, vt;
     bvh::build_triangles(f->verts, f->faces, F, tt);
     bvh::build_points(f->verts, Nv, vt);
+    std::vector<float> tlb;
+    bvh::triangle_node_bounds(tt, f->verts, f->faces, tlb);
 
     // per-primitive records in leaf order (see FrameDev); b - a and c - a are rounded once, exactly like xsub
     std::vector<float> trec((size_t)tt.prims.size() * 4 * TRI_REC_F4), vrec((size_t)vt.prims.size() * 4);
@@ -298,6 +300,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     ENSURE(ctx, ctx->vtx_nodes, vt.nodes.size() * 4); ENSURE(ctx, ctx->vtx_prims, vt.prims.size() * 4);
     ENSURE(ctx, ctx->kpt_cam, kc.size() * 4);
     ENSURE(ctx, ctx->tri_rec, trec.size() * 4); ENSURE(ctx, ctx->vtx_rec, vrec.size() * 4);
+    ENSURE(ctx, ctx->tri_node_lb, tlb.size() * 4);
     ENSURE(ctx, ctx->xyz_ndc, (size_t)V * Nv * 12); ENSURE(ctx, ctx->xy11, (size_t)V * Nv * 8);
     ENSURE(ctx, ctx->zbuf, (size_t)V * RASTER_S * RASTER_S * 8);
 
@@ -310,6 +313,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kpt_cam.p, kc.data(), kc.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_rec.p, trec.data(), trec.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_rec.p, vrec.data(), vrec.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_node_lb.p, tlb.data(), tlb.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(stream));       // pageable host staging above goes out of scope
 
     fr.geo0 = (const float*)ctx->geo0.p; fr.geo1 = (const float*)ctx->geo1.p; fr.tex = (const float*)ctx->tex.p;
@@ -318,6 +322,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     fr.vis = (const float*)ctx->vis.p;
     fr.verts = (const float*)ctx->verts.p; fr.faces = (const int*)ctx->faces.p;
     fr.tri_nodes = (const float4*)ctx->tri_nodes.p; fr.tri_prims = (const int*)ctx->tri_prims.p;
+    fr.tri_node_lb = (const float4*)ctx->tri_node_lb.p;
     fr.vtx_nodes = (const float4*)ctx->vtx_nodes.p; fr.vtx_prims = (const int*)ctx->vtx_prims.p;
     fr.kpt_cam = (const float*)ctx->kpt_cam.p;
     fr.tri_rec = (const float4*)ctx->tri_rec.p; fr.vtx_rec = (const float4*)ctx->vtx_rec.p;
