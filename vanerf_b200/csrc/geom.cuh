@@ -4,10 +4,17 @@
 // 2 + 3 times per pass by brute force (N x F).  Here: one BVH traversal each, with conservative pruning so that
 // the result is identical to the brute-force first-minimum of oracle/geom_oracle.c (ties -> lowest index).
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 #include "rays.cuh"
 
 #define BVH_STACK 48
+#ifdef GEOM_COUNT            // developer build: traversal statistics (printed by k_geom_print after every query launch)
+__device__ unsigned long long d_geom_cnt[8];   // samples, tri nodes popped, past box, past slab, tri slab tests, exact tests, vtx nodes, parity tris
+#define GC(i, n) cnt[i] += (n)
+#else
+#define GC(i, n) ((void)0)
+#endif
 #ifndef GEOM_NODE_LB
 #define GEOM_NODE_LB 1       // per-node slab bound (plane + thickness + bounding circle) after the box test
 #endif
@@ -83,7 +90,8 @@ __device__ __forceinline__ float aabb_dist2(const float4& mn, const float4& mx, 
 
 // bound_d: an upper bound of the result (squared distance to any mesh vertex, slightly inflated by the caller) or +inf.
 // It only prunes: the first-minimum face is still found and its distance is the one point_tri_dist2 computes.
-__device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p, float bound_d, float& best_d, int& best_f) {
+__device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p, float bound_d, float& best_d, int& best_f, unsigned* cnt) {
+    (void)cnt;
     int stack[BVH_STACK];
     int sp = 0;
     stack[sp++] = 0;
@@ -92,7 +100,9 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
     while (sp > 0) {
         const int ni = stack[--sp];
         const float4 mn = fr.tri_nodes[2 * ni], mx = fr.tri_nodes[2 * ni + 1];
+        GC(1, 1);
         if (aabb_dist2(mn, mx, p) > best_d * 1.00001f + 1e-12f) continue;
+        GC(2, 1);
 #if GEOM_NODE_LB
         {   // slab bound of the node (bvh::triangle_node_bounds): for a smooth patch far from p it is much tighter than the
             // box, whose slack lets every node within ~sqrt(2 D size) of the foot point through
@@ -104,11 +114,13 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
             if (u * u + s * s > best_d * 1.0001f + 1e-10f) continue;
         }
 #endif
+        GC(3, 1);
         const int a = __float_as_int(mn.w), b = __float_as_int(mx.w);
         if (a < 0) {
             const int first = ~a;
             for (int i = 0; i < b; ++i) {
                 const float4* rec = fr.tri_rec + TRI_REC_F4 * (first + i);
+                GC(4, 1);
 #if GEOM_TRI_LB
                 {   // Lower bound of the distance to the triangle: it lies in its plane (unit normal n, through c) inside
                     // the circle (c, r), so dist^2 >= h^2 + max(0, sqrt(|p - c|^2 - h^2) - r)^2 with h = n . (p - c).
@@ -125,6 +137,7 @@ __device__ __forceinline__ void closest_face(const FrameDev& fr, const float* p,
 #endif
                 const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
                 const float4 r3 = rec[3];
+                GC(5, 1);
                 const int f = __float_as_int(r0.w);
                 const float va[3] = {r0.x, r0.y, r0.z}, vb[3] = {r1.x, r1.y, r1.z}, vc[3] = {r2.x, r2.y, r2.z};
                 const float d = point_tri_dist2(p, va, vb, vc, r1.w, r2.w, r3.x, r3.y, r3.z, r3.w);
@@ -260,13 +273,15 @@ __global__ void __launch_bounds__(128, GEOM_MINB) k_geom_query(FrameDev fr, Targ
 #ifndef GEOM_ABLATE
 #define GEOM_ABLATE 0        // developer timing experiments (wrong results): 1 no nearest vertex, 2 no closest face, 4 no parity
 #endif
+    unsigned cnt[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    (void)cnt;
     float dnn2 = 1e-4f;
     int nnv = 0;
     if (!(GEOM_ABLATE & 1)) nnv = nearest_vertex(fr, p, dnn2);
     float d2 = 1e-4f; int f = 0;
     if (!(GEOM_ABLATE & 2)) {
-        closest_face(fr, p, dnn2 * 1.0001f + 1e-12f, d2, f);
-        if (f == 0x7fffffff) closest_face(fr, p, __int_as_float(0x7f800000), d2, f);     // never expected; keeps the result exact
+        closest_face(fr, p, dnn2 * 1.0001f + 1e-12f, d2, f, cnt);
+        if (f == 0x7fffffff) closest_face(fr, p, __int_as_float(0x7f800000), d2, f, cnt);     // never expected; keeps the result exact
     }
     const bool in = (GEOM_ABLATE & 4) ? false : inside_parity(fr, p);
     // pts_sdf = sqrt(d2 + 1e-6) * (-2 * (inside - 0.5))   (mesh_util.py:510-512)
@@ -285,4 +300,14 @@ __global__ void __launch_bounds__(128, GEOM_MINB) k_geom_query(FrameDev fr, Targ
             qvis[(size_t)v * N + n] = blend >= 1e-1f ? 1 : 0;
         }
     }
+#ifdef GEOM_COUNT
+    for (int i = 0; i < 8; ++i) if (cnt[i]) atomicAdd(&d_geom_cnt[i], (unsigned long long)cnt[i]);
+#endif
 }
+#ifdef GEOM_COUNT
+__global__ void k_geom_print() {
+    const double n = (double)d_geom_cnt[0];
+    printf("GEOM_COUNT samples %llu per sample: tri nodes popped %.1f past box %.1f past slab %.1f tri slab tests %.1f exact tests %.1f\n",
+           d_geom_cnt[0], d_geom_cnt[1] / n, d_geom_cnt[2] / n, d_geom_cnt[3] / n, d_geom_cnt[4] / n, d_geom_cnt[5] / n);
+}
+#endif

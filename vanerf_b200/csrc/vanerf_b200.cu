@@ -398,6 +398,9 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
     VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, (const float*)nullptr, R, S, pts,
                   sdf, face, nn_vert, qvis);
     CHECK_LAUNCH(ctx);
+#ifdef GEOM_COUNT
+    VANERF_LAUNCH(k_geom_print, 1, 1, 0, stream);
+#endif
     return VANERF_OK;
 }
 
