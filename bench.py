@@ -234,6 +234,7 @@ def main():
     ap.add_argument("--workload", default="B", choices=["B", "C", "D"])
     ap.add_argument("--frames", type=int, default=8, help="workload D: frames per step (BASELINE.json configs[3] uses 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reuse-variant", action="store_true", help="skip the secondary coarse-reuse measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -370,6 +371,25 @@ def main():
         fp32_extra = {"ms_per_view": a.elapsed_time(b), "value": H * W / (a.elapsed_time(b) * 1e-3), "unit": "rays/s",
                       "note": "fp32 FFMA path (k_gather + k_mlp_simt), 1 warm-up + 1 timed view, inputs resident"}
 
+    # ---------------- coarse reuse (vanerf_set_reuse_coarse): same output bits, 64 + 64 instead of 64 + 128 evaluations per ray
+    reuse_extra = None
+    if world == 1 and not args.no_reuse_variant:
+        r.set_reuse_coarse(True)
+        r.render_rays(tar, pix, S_C, S_F, True, prec)
+        torch.cuda.synchronize()
+        evr = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(max(1, args.steps))]
+        for a, b in evr:
+            flush.fill_(1)
+            a.record()
+            r.render_rays(tar, pix, S_C, S_F, True, prec)
+            b.record()
+        torch.cuda.synchronize()
+        r.set_reuse_coarse(False)
+        ms_r = sum(a.elapsed_time(b) for a, b in evr) / len(evr)
+        reuse_extra = {"ms_per_view": ms_r, "value": H * W / (ms_r * 1e-3), "unit": "rays/s", "evaluations_per_ray": S_C + S_F,
+                       "note": "NOT the headline: fine pass evaluates only the 64 new depths and reuses the coarse pass for the 64 coarse "
+                               "depths of the merged set (bit-identical output, tests: *_coarse_reuse_is_bit_identical); inputs resident"}
+
     if rank == 0:
         pk = peaks()
         clk = clocks.stop()
@@ -402,6 +422,8 @@ def main():
         }
         if fp32_extra is not None:
             line["fp32_path"] = fp32_extra
+        if reuse_extra is not None:
+            line["coarse_reuse"] = reuse_extra
         if world == 1 and not args.no_cpu_baseline:
             rps, sec, n = cpu_port_rays_per_s(32, False)
             line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",

@@ -156,6 +156,13 @@ int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar,
                        int32_t n_rays, int32_t n_coarse, int32_t n_fine, int32_t fine, const float* ztab,
                        const float* utab, float* out_coarse, float* out_fine, void* stream);
 
+/* Coarse reuse in vanerf_render_rays (default off = the reference's evaluation count).  The merged fine set of
+ * src/model.py:1301-1307 contains the n_coarse coarse depths bit for bit and a sample's outputs depend only on its
+ * point and ray, so the reference evaluates those samples twice (:1280-1294 and :1340-1349).  With reuse on, only the
+ * n_fine new depths go through geometry / gather / networks in the fine pass and the merged arrays are assembled from
+ * the two evaluations: identical output bits, n_coarse + n_fine instead of 2 n_coarse + n_fine evaluations per ray. */
+int vanerf_set_reuse_coarse(vanerf_ctx* ctx, int on);
+
 /* Scratch the context needs for vanerf_render_rays / vanerf_shade at the given sizes (bytes). */
 size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t n_rays, int32_t n_samples);
 

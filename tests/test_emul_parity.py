@@ -39,3 +39,21 @@ def test_emulated_ragged_sizes(emul_lib):
     rgba, valid, raw = r.shade(tar, rays, z, geo)
     parity.assert_exact("valid", valid.numpy() > 0, ot["valid"])
     parity.assert_close("rgba", rgba.numpy(), ot["rgba"], parity.TOL_FP32)
+
+
+def test_emulated_coarse_reuse_is_bit_identical(emul_lib):
+    """vanerf_set_reuse_coarse: the fine pass evaluates only the new depths and reuses the coarse pass for the coarse
+    depths inside the merged set; the rendered rows must not change by a single bit (logic check on the emulated
+    kernels; the GPU suite repeats it for both precision paths)."""
+    import torch
+    sc, inp, sd = parity.build_case(256, 256, 2, mode="stress")
+    r, _ = parity.make_renderer(inp, sd, "cpu", emul_lib)
+    pix = torch.from_numpy(parity.lattice_pixels(256, 256, 3)[:7])
+    tar = r.make_target(inp["cam_tar"], inp["bounds"])
+    oc0, of0 = r.render_rays(tar, pix, 24, 16, True, L.FP32)
+    oc0, of0 = oc0.clone(), of0.clone()
+    r.set_reuse_coarse(True)
+    oc1, of1 = r.render_rays(tar, pix, 24, 16, True, L.FP32)
+    r.set_reuse_coarse(False)
+    assert torch.equal(oc0, oc1) and torch.equal(of0, of1)
+    assert torch.isfinite(of1).all() and float(of1[:, :3].abs().max()) > 0

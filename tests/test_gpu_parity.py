@@ -147,3 +147,23 @@ def test_cuda_render_sequence_frames_are_independent(cuda_lib):
         ids_r, out_r = dynamic.render_sequence(make_net(), lambda f: frames[f], F, lambda f: [cams[f]], rank, 2, **cfg)
         got.update(dict(zip(ids_r, out_r)))
     assert sorted(got) == list(range(F)) and all(torch.equal(got[f], seq[f]) for f in range(F))
+
+
+@pytest.mark.parametrize("precision", [L.FP32, L.BF16])
+def test_cuda_coarse_reuse_is_bit_identical(cuda_lib, precision):
+    """vanerf_set_reuse_coarse on the real library, both precision paths: same output bits with a third fewer network
+    evaluations per ray (the merged fine set contains the coarse depths bit for bit; a sample's result does not depend
+    on which tile or launch evaluates it)."""
+    sc, inp, sd = parity.build_case(512, 334, 3, mode="stress")
+    r, _ = parity.make_renderer(inp, sd, "cuda:0")
+    pix = torch.from_numpy(parity.lattice_pixels(512, 334, 24))
+    tar = r.make_target(inp["cam_tar"], inp["bounds"])
+    oc0, of0 = r.render_rays(tar, pix, 64, 64, True, precision)
+    oc0, of0 = oc0.clone(), of0.clone()
+    n0 = r.launches
+    r.set_reuse_coarse(True)
+    oc1, of1 = r.render_rays(tar, pix, 64, 64, True, precision)
+    r.set_reuse_coarse(False)
+    assert r.launches > n0
+    assert torch.equal(oc0, oc1) and torch.equal(of0, of1)
+    assert torch.isfinite(of1).all() and float(of1[:, :3].abs().max()) > 0

@@ -83,7 +83,8 @@ k_composite(const float* __restrict__ rgba, const float* __restrict__ z, const f
 // One warp per ray.  Dynamic shared memory per warp: cdf[S-1] | zmid[S-1] | vals[S+nf]  (floats).
 __global__ void __launch_bounds__(COMP_WARPS * 32)
 k_importance(const float* __restrict__ contrib, const float* __restrict__ z, const float* __restrict__ zmid_in, int R, int S,
-             const float* __restrict__ u, int nf, int u_per_ray, float* __restrict__ z_fine_only, float* __restrict__ z_out) {
+             const float* __restrict__ u, int nf, int u_per_ray, float* __restrict__ z_fine_only, float* __restrict__ z_out,
+             unsigned char* __restrict__ src_map) {      // optional (R, S + nf): merged slot -> index into [z | z_fine]
     DYN_SMEM(float, sm);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int per_warp = 2 * (S - 1) + (S + nf);
@@ -146,9 +147,29 @@ k_importance(const float* __restrict__ contrib, const float* __restrict__ z, con
                 const float y = vals[j];
                 rank += (y < x || (y == x && j < i)) ? 1 : 0;
             }
-            if (live) z_out[(size_t)r * n + rank] = x;
+            if (live) {
+                z_out[(size_t)r * n + rank] = x;
+                if (src_map) src_map[(size_t)r * n + rank] = (unsigned char)i;
+            }
         }
     }
+}
+
+// Merged fine-pass inputs of rgba2out from the two places they were evaluated (coarse reuse, see vanerf_render_rays):
+// slot k of ray r comes from coarse sample src < S (rgba_c, sdf_c) or from new fine sample src - S (rgba_f, sdf_f).
+__global__ void k_merge_reuse(const unsigned char* __restrict__ src_map, const float* __restrict__ rgba_c, const float* __restrict__ sdf_c,
+                              const float* __restrict__ rgba_f, const float* __restrict__ sdf_f, int R, int S, int nf,
+                              float* __restrict__ rgba_m, float* __restrict__ sdf_m) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S + nf;
+    if (k >= (long long)R * n) return;
+    const int r = (int)(k / n), src = src_map[k];
+    const bool c = src < S;
+    const size_t j = c ? (size_t)r * S + src : (size_t)r * nf + (src - S);
+    const float* q = (c ? rgba_c : rgba_f) + 5 * j;
+    float* o = rgba_m + 5 * (size_t)k;
+    o[0] = q[0]; o[1] = q[1]; o[2] = q[2]; o[3] = q[3]; o[4] = q[4];
+    sdf_m[k] = (c ? sdf_c : sdf_f)[j];
 }
 
 // planes: color (stride,3) | depth (stride) | alpha (stride) | sdf (stride)  ->  rows (n,8) = r,g,b,depth,alpha,sdf,0,0

@@ -61,6 +61,9 @@ struct vanerf_ctx {
         kpt_cam, xyz_ndc, xy11, zbuf, tri_rec, vtx_rec, tri_node_lb;
     // scratch
     DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
+    DevBuf s_zf, s_srcmap, s_sdf_f, s_rgba_f, s_sdf_m, s_rgba_m;      // coarse reuse (vanerf_set_reuse_coarse)
+    bool reuse_coarse = false;
+    unsigned char* imp_src_map = nullptr;   // set around the importance launch of vanerf_render_rays (coarse reuse)
 };
 
 static int ctx_fail(vanerf_ctx* ctx, cudaError_t e, const char* what, int line) {
@@ -134,7 +137,8 @@ void vanerf_ctx_destroy(vanerf_ctx* c) {
     DevBuf* all[] = {&c->wblob, &c->netdev, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
                      &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
                      &c->xyz_ndc, &c->xy11, &c->zbuf, &c->tri_rec, &c->vtx_rec, &c->tri_node_lb, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
-                     &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab};
+                     &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab,
+                     &c->s_zf, &c->s_srcmap, &c->s_sdf_f, &c->s_rgba_f, &c->s_sdf_m, &c->s_rgba_m};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     delete c;
 }
@@ -722,8 +726,15 @@ int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int
     if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
     TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
-    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, zmid_in, R, S, u, nf, u_per_ray, z_fine_only, z_out);
+    VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, zmid_in, R, S, u, nf, u_per_ray, z_fine_only, z_out,
+                  ctx->imp_src_map);
     CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+int vanerf_set_reuse_coarse(vanerf_ctx* ctx, int on) {
+    if (!ctx) return VANERF_ERR_INVALID;
+    ctx->reuse_coarse = on != 0;
     return VANERF_OK;
 }
 
@@ -737,7 +748,7 @@ int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const flo
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
     TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib_inner, (const float*)nullptr, z_mid, R, D, u, nf,
-                  u_per_ray, z_fine, (float*)nullptr);
+                  u_per_ray, z_fine, (float*)nullptr, (unsigned char*)nullptr);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
 }
@@ -787,10 +798,32 @@ int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar,
         VANERF_LAUNCH(k_pack_out, cdiv(rc, 256), 256, 0, stream, pl, RC, rc, oc); CHECK_LAUNCH(ctx);
         if (fine) {
             float* of = out_fine + (size_t)r0 * 8;
+            if (ctx->reuse_coarse) {
+                // The merged fine set contains the Sc coarse depths bit for bit, and a sample's outputs depend on nothing
+                // but its point and ray: the reference re-evaluates those Sc samples (src/model.py:1301-1349), here only
+                // the Sf new depths go through geometry / gather / networks and the merged arrays are assembled from the
+                // two evaluations (k_merge_reuse).  Same bits out, a third fewer evaluations per ray.
+                ENSURE(ctx, ctx->s_zf, (size_t)RC * Sf * 4); ENSURE(ctx, ctx->s_srcmap, Nmax);
+                ENSURE(ctx, ctx->s_sdf_f, (size_t)RC * Sf * 4); ENSURE(ctx, ctx->s_rgba_f, (size_t)RC * Sf * 20);
+                ENSURE(ctx, ctx->s_sdf_m, Nmax * 4); ENSURE(ctx, ctx->s_rgba_m, Nmax * 20);
+                float* zf = (float*)ctx->s_zf.p; float* sdf_f = (float*)ctx->s_sdf_f.p; float* rgba_f = (float*)ctx->s_rgba_f.p;
+                float* sdf_m = (float*)ctx->s_sdf_m.p; float* rgba_m = (float*)ctx->s_rgba_m.p;
+                ctx->imp_src_map = (unsigned char*)ctx->s_srcmap.p;
+                st = vanerf_importance(ctx, contrib, z, rc, Sc, utab, Sf, 0, zf, z2, stream_);
+                ctx->imp_src_map = nullptr;
+                if (st) return st;
+                if ((st = vanerf_geom_query(ctx, tar, rays, zf, rc, Sf, nullptr, sdf_f, nullptr, nn, qv, stream_))) return st;
+                if ((st = shade_impl(ctx, precision, td, rays, zf, rc, Sf, sdf_f, nn, qv, rgba_f, nullptr, nullptr, nullptr, stream))) return st;
+                VANERF_LAUNCH(k_merge_reuse, cdiv((long long)rc * S2, 256), 256, 0, stream, (const unsigned char*)ctx->s_srcmap.p, rgba, sdf,
+                              rgba_f, sdf_f, rc, Sc, Sf, rgba_m, sdf_m);
+                CHECK_LAUNCH(ctx);
+                if ((st = vanerf_composite(ctx, rgba_m, z2, sdf_m, rc, S2, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, nullptr, stream_))) return st;
+            } else {
             if ((st = vanerf_importance(ctx, contrib, z, rc, Sc, utab, Sf, 0, nullptr, z2, stream_))) return st;
             if ((st = vanerf_geom_query(ctx, tar, rays, z2, rc, S2, nullptr, sdf, nullptr, nn, qv, stream_))) return st;
             if ((st = shade_impl(ctx, precision, td, rays, z2, rc, S2, sdf, nn, qv, rgba, nullptr, nullptr, nullptr, stream))) return st;
             if ((st = vanerf_composite(ctx, rgba, z2, sdf, rc, S2, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, nullptr, stream_))) return st;
+            }
             VANERF_LAUNCH(k_pack_out, cdiv(rc, 256), 256, 0, stream, pl, RC, rc, of); CHECK_LAUNCH(ctx);
         }
     }

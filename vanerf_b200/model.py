@@ -193,6 +193,9 @@ class VANeRF:
         vert_vis = net._ensure_frame(img_in, cam_in, targets, sp_data, feat_geo, feat_tex, config["src_foreground_mask"])
         r = net.renderer
         tar = r.make_target(cam_tar, config["bounds"], cam_tar.get("znear", cam_in["znear"]), cam_tar.get("zfar", cam_in["zfar"]))
+        # reuse_coarse (extension, default False = the reference's evaluation count): identical output bits, the fine pass
+        # evaluates only the S_f new depths (Renderer.set_reuse_coarse)
+        r.set_reuse_coarse(bool(config.get("reuse_coarse", False)))
         oc, of = r.render_rays(tar, grids, S_c, S_f, fine, net.precision)
         img = lambda t, c: t.reshape(out_h, out_w, c).permute(2, 0, 1)[None]
         out = {"tex_fg": img(oc[:, :3], 3), "depth": oc[:, 3].reshape(1, out_h, out_w), "alpha": oc[:, 4].reshape(1, out_h, out_w)}
