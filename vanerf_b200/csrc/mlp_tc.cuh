@@ -63,9 +63,6 @@
 #endif
 #define TC_SMEM_BYTES (TC_OFF_TRACE + TC_TRACE_N * 8)
 
-#ifndef TC_ROLL_GATES
-#define TC_ROLL_GATES 0                  // the twelve in-place gate multiplications of GeoVisFusion as one loop body
-#endif
 #ifndef TC_ROLL_MLP
 #define TC_ROLL_MLP 1                    // the three 128-wide Softplus epilogues of MLPUNet layers1 share one loop body
 #endif
@@ -1037,19 +1034,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         for (int i = 0; i < 10; ++i) s = fmaf(w[i], fmaxf(hid[i], 0.0f), s);
                         g8[j] = tc_act<TA_SIGMOID>(s);
                     }
-#if TC_ROLL_GATES
-#pragma unroll 1
-                    for (int s = 0; s < 3; ++s) {
-                        const float gs = tc_sel3(g64, s);
-#pragma unroll 1
-                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, gs);
-                    }
-#else
 #pragma unroll
                     for (int s = 0; s < 3; ++s)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g64[s]);
-#endif
                     if (h == 0) t.gate_chunk1(3, 2, g8[0]);
                     else { t.gate_chunk1(3, 3, g8[1]); t.gate_chunk1(3, 4, g8[2]); }
                 }
