@@ -17,6 +17,7 @@
 #define TS 64               // samples per tile
 #define KC 16               // weight rows staged per chunk
 #define WS_FLOATS (KC * 128)
+static_assert(KC * 128 / 4 <= 2 * MLP_THREADS, "gemm_acc stages a weight chunk with two float4 per thread");
 
 enum Act { ACT_NONE = 0, ACT_RELU, ACT_SOFTPLUS, ACT_SIGMOID, ACT_ELU };
 
@@ -35,13 +36,31 @@ __device__ __forceinline__ void gemm_acc(float (&acc)[4][8], const float* A, int
                                          int Npad, float* WS) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const bool active = 8 * ty < Npad;
+    // Weight chunks (KC rows of Npad <= 128 floats = at most two float4 per thread) go global -> registers -> shared: the
+    // loads of chunk i + 1 are issued before the FMAs of chunk i, so their L2 latency hides behind the arithmetic instead
+    // of sitting between two block barriers in front of every chunk.
+    float4 pre[2];
+    auto fetch = [&](int k0) {
+        const int n4 = (min(KC, K - k0) * Npad) >> 2;
+        const float4* src = reinterpret_cast<const float4*>(Wt + (size_t)k0 * Npad);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + j * MLP_THREADS;
+            pre[j] = i < n4 ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < K; k0 += KC) {
         const int kc = min(KC, K - k0);
-        __syncthreads();
         const int n4 = (kc * Npad) >> 2;
-        const float4* src = reinterpret_cast<const float4*>(Wt + (size_t)k0 * Npad);
-        for (int i = tid; i < n4; i += MLP_THREADS) reinterpret_cast<float4*>(WS)[i] = src[i];
+        __syncthreads();                                   // readers of the previous chunk are done
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = tid + j * MLP_THREADS;
+            if (i < n4) reinterpret_cast<float4*>(WS)[i] = pre[j];
+        }
         __syncthreads();
+        if (k0 + KC < K) fetch(k0 + KC);
         if (active) {
             for (int k = 0; k < kc; ++k) {
                 const float4 a = *reinterpret_cast<const float4*>(A + (size_t)(k0 + k) * TS + 4 * tx);
