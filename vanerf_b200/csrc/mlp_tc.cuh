@@ -10,13 +10,15 @@
 // One CTA per SM works on TWO 128-sample tiles at a time (persistent over tile pairs): each tile has its own group of
 // 8 warps (two threads per row: warps w and w+4 of the group share the TMEM lane quarter w and split the columns), its
 // own five 16 KB operand slots (128 rows x 64 bf16, K-major, 128B swizzle), its own accumulator / pooling TMEM columns
-// ([0,128) / [128,256) of its 256-column half) and its own barriers, and runs the layer sequence independently, so one
-// tile's epilogue overlaps the other's MMAs.  Both tiles consume the SAME weight stream: one producer warp brings the
-// weight images in once per tile pair through a 3 x 16 KB ring (cp.async.bulk + mbarriers; a ring slot is released when
-// the MMAs of both tiles that read it have completed).  Activations never leave the SM.  Step tables, biases and the
-// camera-space keypoints are copied to shared memory once per CTA.
-// The layer sequence is a table of "steps" (a set of MMAs whose results are consumed by one epilogue) built on the
-// host together with the weight images, so that the packer, the producer and the issuer cannot disagree.
+// ([0,128) / [128,256) of its 256-column half), its own MMA issuer warp and its own barriers, and runs the layer
+// sequence independently, so one tile's epilogue can overlap the other's MMAs.  Both tiles consume the SAME weight
+// stream: one producer lane brings the weight images in once per tile pair through a 4 x 16 KB ring (cp.async.bulk +
+// mbarriers; a ring slot is released when the MMAs of both tiles that read it have completed).  Activations never leave
+// the SM.  Biases, the small fp32 layers and the camera-space keypoints travel as a kernel parameter (constant bank).
+// The layer sequence is a table of "steps" (a set of MMAs whose results are consumed by one epilogue), known at compile
+// time (kProg) and rebuilt on the host together with the weight images, so that the packer, the producer and the issuer
+// cannot disagree.  Code size is a first-order cost of this kernel (it streams its instructions from L2): see the notes
+// at TC_ROLL_VIEWS / TC_ROLL_MLP / tc_issuer_warp and DESIGN.md section 5.
 #pragma once
 #include <algorithm>
 #include "common.cuh"
