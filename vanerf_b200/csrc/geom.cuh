@@ -15,6 +15,9 @@ __device__ unsigned long long d_geom_cnt[8];   // samples, tri nodes popped, pas
 #else
 #define GC(i, n) ((void)0)
 #endif
+#ifndef GEOM_RAY_LANES
+#define GEOM_RAY_LANES 8       // rays per warp (sweep: 32 -> 30.0 ms, 16 -> 26.4, 8 -> 25.5, 4 -> 26.4; 0 = old mapping, 32 depths of one ray: 35.0)
+#endif
 #ifndef GEOM_NODE_LB
 #define GEOM_NODE_LB 1       // per-node slab bound (plane + thickness + bounding circle) after the box test
 #endif
@@ -259,8 +262,25 @@ __device__ __forceinline__ void bary_of_projection(const FrameDev& fr, const flo
 __global__ void __launch_bounds__(128, GEOM_MINB) k_geom_query(FrameDev fr, TargetDev tar, const float* __restrict__ rays, const float* __restrict__ z,
                              const float* __restrict__ pts_in, int R, int S, float* __restrict__ pts, float* __restrict__ sdf,
                              int* __restrict__ face, int* __restrict__ nn_vert, unsigned char* __restrict__ qvis) {
-    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long N = (long long)R * S;
+    long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+#if GEOM_RAY_LANES
+    // Thread -> sample mapping for ray batches: the 32 lanes of a warp take the SAME depth index of 32 consecutive rays
+    // (neighbouring pixels: a few millimetres apart in space), consecutive warps the next depth index.  With 32 consecutive
+    // depths of one ray per warp the lanes were up to 11 cm apart and every lane walked its own BVH path; now the warp
+    // walks (nearly) one path.  Results do not depend on the mapping; outputs stay indexed by n = ray * S + depth.
+    if (!pts_in) {
+        // a warp = GEOM_RAY_LANES consecutive rays x (32 / GEOM_RAY_LANES) consecutive depth indices
+        constexpr int RL = GEOM_RAY_LANES, DL = 32 / RL;
+        const long long gw = n >> 5;
+        const int lane = (int)(n & 31);
+        const int sb_per_ray_block = (S + DL - 1) / DL;
+        const int rb = (int)(gw / sb_per_ray_block), sb = (int)(gw - (long long)rb * sb_per_ray_block);
+        const int rr = rb * RL + (lane % RL), si = sb * DL + lane / RL;
+        if (rr >= R || si >= S) return;
+        n = (long long)rr * S + si;
+    }
+#endif
     if (n >= N) return;
     const int r = (int)(n / S);
     float p[3];

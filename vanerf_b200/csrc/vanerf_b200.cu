@@ -399,7 +399,13 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
     if (!ctx->have_frame) return VANERF_ERR_STATE;
     const long long N = (long long)R * S;
     TimedScope ts(ctx, KCL_GEOM, (cudaStream_t)stream);
-    VANERF_LAUNCH(k_geom_query, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, (const float*)nullptr, R, S, pts,
+    // ray batches: one warp per (block of 32 rays, depth index), see GEOM_RAY_LANES in geom.cuh
+#if GEOM_RAY_LANES
+    const long long n_thr = (long long)cdiv(R, GEOM_RAY_LANES) * cdiv(S, 32 / GEOM_RAY_LANES) * 32;
+#else
+    const long long n_thr = N;
+#endif
+    VANERF_LAUNCH(k_geom_query, cdiv(n_thr, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, (const float*)nullptr, R, S, pts,
                   sdf, face, nn_vert, qvis);
     CHECK_LAUNCH(ctx);
 #ifdef GEOM_COUNT
