@@ -16,5 +16,5 @@ for f in ('gpurun_out/bench_bf16.json','gpurun_out/bench_reference.json'):
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_bf16.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-fp32-path > gpurun_out/ncu_list_bf16.log 2>&1; echo "ncu list exit $?"
 timeout 200 python tools/prof_small.py --rays 8192 --precision bf16 > gpurun_out/prof_small_bf16_plain.log 2>&1 &&
-timeout 800 ncu --set full --clock-control none --import-source on -k regex:'k_mlp_tc|k_gather_tc|k_geom_query' -s 3 -c 6 -o gpurun_out/prof_bf16_r6 -f python tools/prof_small.py --rays 8192 --precision bf16 > gpurun_out/ncu_full_bf16.log 2>&1
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:'k_mlp_tc|k_gather_tc|k_geom_query' -s 3 -c 6 -o gpurun_out/prof_bf16_r7 -f python tools/prof_small.py --rays 8192 --precision bf16 > gpurun_out/ncu_full_bf16.log 2>&1
 echo "ncu full exit $?"

@@ -397,13 +397,12 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
                       float* pts, float* sdf, int32_t* face, int32_t* nn_vert, uint8_t* qvis, void* stream) {
     if (!ctx || !tar || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_geom_query");
     if (!ctx->have_frame) return VANERF_ERR_STATE;
-    const long long N = (long long)R * S;
     TimedScope ts(ctx, KCL_GEOM, (cudaStream_t)stream);
     // ray batches: one warp per (block of 32 rays, depth index), see GEOM_RAY_LANES in geom.cuh
 #if GEOM_RAY_LANES
     const long long n_thr = (long long)cdiv(R, GEOM_RAY_LANES) * cdiv(S, 32 / GEOM_RAY_LANES) * 32;
 #else
-    const long long n_thr = N;
+    const long long n_thr = (long long)R * S;
 #endif
     VANERF_LAUNCH(k_geom_query, cdiv(n_thr, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, (const float*)nullptr, R, S, pts,
                   sdf, face, nn_vert, qvis);
