@@ -72,7 +72,9 @@ __device__ __forceinline__ uint4 tap8_bf16(const __nv_bfloat16* __restrict__ map
     return pack8(o);
 }
 
+#ifndef GTC_THREADS
 #define GTC_THREADS 256
+#endif
 #ifndef GTC_MINB
 #define GTC_MINB 4                      // resident CTAs per SM the register allocation aims for
 #endif
