@@ -163,6 +163,14 @@ int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar,
  * the two evaluations: identical output bits, n_coarse + n_fine instead of 2 n_coarse + n_fine evaluations per ray. */
 int vanerf_set_reuse_coarse(vanerf_ctx* ctx, int on);
 
+/* Geometry reuse in the fine pass of vanerf_render_rays (default ON).  The mesh queries of the reference
+ * (cal_vis_sdf_batch mesh_util.py:498-524, knn_points networks.py:28) are functions of the sample position alone and the
+ * merged fine set holds the n_coarse coarse depths bit for bit, so the fine pass queries the mesh for the n_fine new
+ * depths only and takes the coarse pass's sdf / nearest vertex / sample visibility for the rest.  The NETWORKS still
+ * evaluate all n_coarse + n_fine merged samples, as the reference does (src/model.py:1328-1349): same evaluation count,
+ * identical output bits (tests: *_geometry_reuse_is_bit_identical).  0 = query the mesh again for every merged sample. */
+int vanerf_set_reuse_geometry(vanerf_ctx* ctx, int on);
+
 /* Scratch the context needs for vanerf_render_rays / vanerf_shade at the given sizes (bytes). */
 size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t n_rays, int32_t n_samples);
 

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "vanerf_importance": (C.c_int, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P, _P]),
     "vanerf_importance_mid": (C.c_int, [_P, _P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "vanerf_set_reuse_coarse": (C.c_int, [_P, C.c_int]),
+    "vanerf_set_reuse_geometry": (C.c_int, [_P, C.c_int]),
     "vanerf_render_rays": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "vanerf_query_points": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "vanerf_timing_enable": (C.c_int, [_P, C.c_int]),

@@ -157,6 +157,26 @@ k_importance(const float* __restrict__ contrib, const float* __restrict__ z, con
 
 // Merged fine-pass inputs of rgba2out from the two places they were evaluated (coarse reuse, see vanerf_render_rays):
 // slot k of ray r comes from coarse sample src < S (rgba_c, sdf_c) or from new fine sample src - S (rgba_f, sdf_f).
+// Geometry of the merged fine set assembled from the coarse pass and the new depths (vanerf_render_rays): merged slot k of
+// ray r takes sdf / nearest vertex / per-view sample visibility from index src_map[k] of [coarse | new].  The merged set
+// contains the coarse depths bit for bit (sort of cat[z, z_fine], src/model.py:1301-1307) and the mesh queries depend on
+// the sample position only, so this is the array cal_vis_sdf_batch / knn_points would return for the 128 depths.
+__global__ void k_merge_geom(const unsigned char* __restrict__ src_map, const float* __restrict__ sdf_c, const int* __restrict__ nn_c,
+                             const unsigned char* __restrict__ qv_c, const float* __restrict__ sdf_f, const int* __restrict__ nn_f,
+                             const unsigned char* __restrict__ qv_f, int R, int S, int nf, int V, float* __restrict__ sdf_m,
+                             int* __restrict__ nn_m, unsigned char* __restrict__ qv_m) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = S + nf;
+    if (k >= (long long)R * n) return;
+    const int r = (int)(k / n), src = src_map[k];
+    const bool c = src < S;
+    const size_t j = c ? (size_t)r * S + src : (size_t)r * nf + (src - S);
+    const size_t Nc = (size_t)R * S, Nf = (size_t)R * nf, Nm = (size_t)R * n;
+    sdf_m[k] = c ? sdf_c[j] : sdf_f[j];
+    nn_m[k] = c ? nn_c[j] : nn_f[j];
+    for (int v = 0; v < V; ++v) qv_m[(size_t)v * Nm + k] = c ? qv_c[(size_t)v * Nc + j] : qv_f[(size_t)v * Nf + j];
+}
+
 __global__ void k_merge_reuse(const unsigned char* __restrict__ src_map, const float* __restrict__ rgba_c, const float* __restrict__ sdf_c,
                               const float* __restrict__ rgba_f, const float* __restrict__ sdf_f, int R, int S, int nf,
                               float* __restrict__ rgba_m, float* __restrict__ sdf_m) {

@@ -78,6 +78,15 @@
 #else
 #define TC_VLOOP _Pragma("unroll")
 #endif
+// Measured and dropped (round 2): starting tile group 1 half a step after group 0 (the tiles do not contend for a saturated
+// resource, so their phase does not matter: 88.8 vs 90.6 ms); requesting the next view's operand images two layers early
+// (h2 moved to slots 4 | 0 to free slots 1-3: 93.7 vs 90.7 ms).
+#ifndef TC_F32X2
+#define TC_F32X2 1                       // packed fp32 pairs (FADD2 / FMUL2 / FFMA2) in the epilogues: -4.5 % kernel time
+#endif
+#ifndef TC_PREWAIT
+#define TC_PREWAIT 1                     // issuer waits for a step's weight chunks before it waits for the step's operands: -9 %
+#endif
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
 #endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating
@@ -525,9 +534,7 @@ __device__ __forceinline__ uint32_t tc_softplus2(float a, float b) {
     return r;
 #endif
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
-    asm("{.reg .b32 n;\n\t"
-        "neg.bf16x2 n, %1;\n\t"
-        "min.bf16x2 %0, %1, n;}" : "=r"(na) : "r"(h));                    // -|h|
+    na = h | 0x80008000u;                                                        // -|h|
     asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(w) : "r"(na), "r"(0x43104310u));      // * 144 (100 log2 e)
     asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(w) : "r"(w));
     asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(w), "r"(0x3A933A93u), "r"(0xBB85BB85u));   // c2 = 1.1234e-3, c1 = -4.0516e-3
@@ -552,6 +559,15 @@ __device__ __forceinline__ uint32_t tc_mul2(uint32_t a, uint32_t b) {
     return d;
 }
 __device__ __forceinline__ uint32_t tc_dup_bf16(float g) { return tc::pack_bf16(g, g); }
+// (a * s, b * s) -> packed bf16; with TC_F32X2 the two products are one FMUL2
+__device__ __forceinline__ uint32_t tc_pack_scaled(float a, float b, float s) {
+#if TC_F32X2
+    const float2 p = __fmul2_rn(make_float2(a, b), make_float2(s, s));
+    return tc::pack_bf16(p.x, p.y);
+#else
+    return tc::pack_bf16(a * s, b * s);
+#endif
+}
 
 __device__ __forceinline__ float tc_sel3(const float (&a)[3], int v) { return v == 0 ? a[0] : (v == 1 ? a[1] : a[2]); }
 __device__ __forceinline__ void tc_set3(float (&a)[3], int v, float x) {
@@ -586,10 +602,12 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
         const uint32_t c = cc + op.chunk_rel;
         slot_i = c % TC_NRING;
         bd_slot = bd_base + (uint64_t)(slot_i * (TC_SLOT >> 4));
+#if !TC_PREWAIT
         TC_PROF(7000);
         tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
         tc::tcgen05_fence_after();
         TC_PROF(7100);
+#endif
     }
     // descriptors = base descriptor + (byte offset >> 4): the start-address field (14 bits of address >> 4) cannot
     // carry into its neighbours because every operand lies inside the CTA's 227 KB of shared memory
@@ -603,6 +621,21 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
     }
     if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1>(cc, bd_slot, slot_i, sh, ad_base, bd_base, tmem, lead);
 }
+// Waits for every weight chunk of step ST (TC_PREWAIT): done BEFORE the wait for the step's operands, because the weights
+// are streamed a step ahead and have normally landed long before the tile's epilogue publishes; the ~100-cycle
+// already-complete try_wait per chunk then leaves the tile's critical path.  No deadlock: a chunk's ring slot only
+// depends on MMAs of earlier steps (issued by this warp in program order, by the other tile's issuer at its own pace).
+template <int ST, int I>
+__device__ __forceinline__ void tc_prewait_chunks(uint32_t cc, TcShared* sh) {
+    constexpr TcStep S = kProg.steps[ST];
+    constexpr TcOp op = kProg.ops[S.op0 + I];
+    constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
+    if (first_in_chunk) {
+        const uint32_t c = cc + op.chunk_rel;
+        tc::mbar_wait(&sh->wfull[c % TC_NRING], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
+    }
+    if constexpr (I + 1 < S.nops) tc_prewait_chunks<ST, I + 1>(cc, sh);
+}
 // One step of an MMA issuer warp: wait until the tile's eight warps have published the operands of step number n
 // (and finished reading the accumulators the step overwrites), then issue the step's MMAs and commit.
 // COMMIT: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (COMMIT - 1), -1 = none.
@@ -610,6 +643,10 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
 template <int ST, int COMMIT>
 __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, TcShared* sh, uint32_t act_u32, uint32_t ring_u32,
                                                uint32_t tmem, int tg, bool lead) {
+#if TC_PREWAIT
+    constexpr uint32_t cc_off_pre = kProg.cc_off[ST];
+    tc_prewait_chunks<ST, 0>(cc_base + cc_off_pre, sh);
+#endif
     TC_PROF(8000 + ST);                  // issuer: previous step issued, waiting for this step's operands
     const bool ok = tc::mbar_wait(&sh->ready[tg][n % TC_NREADY], (n / TC_NREADY) & 1, sh->abort_flag, 600 + ST);
     ++n;
@@ -739,8 +776,14 @@ struct TcTile {
 #endif
         float f[8];
         unpack8(ld_chunk(s, chunk), f);
+#if TC_F32X2
+        const float2 g2 = make_float2(g, g);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) { const float2 p = __fmul2_rn(make_float2(f[i], f[i + 1]), g2); f[i] = p.x; f[i + 1] = p.y; }
+#else
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] *= g;
+#endif
         st_chunk(s, chunk, pack8(f));
     }
 };
@@ -752,9 +795,15 @@ __device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const floa
     if (bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 b4 = reinterpret_cast<const float4*>(bias)[i];      // shared memory, warp-uniform address
+            const float4 b4 = reinterpret_cast<const float4*>(bias)[i];      // constant bank, warp-uniform address
+#if TC_F32X2
+            const float2 lo = __fadd2_rn(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(b4.x, b4.y));
+            const float2 hi = __fadd2_rn(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(b4.z, b4.w));
+            v[4 * i] = lo.x; v[4 * i + 1] = lo.y; v[4 * i + 2] = hi.x; v[4 * i + 3] = hi.y;
+#else
             v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+#endif
         }
     } else {
 #pragma unroll
@@ -987,7 +1036,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
         const int row = t.row, h = t.half, tg = t.tg;
         const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
-
 #pragma unroll 1
         for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
             // an odd tile count leaves the last pair's second group without a tile: it re-runs the last tile (the ring
@@ -1077,8 +1125,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
                         const float s2 = 2.0f * s1 * c1, c2 = 1.0f - 2.0f * s1 * s1;
                         const float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
-                        t.st_chunk(pslot, 2 * j + h, make_uint4(tc::pack_bf16(dz * w, s1 * w), tc::pack_bf16(c1 * w, s2 * w),
-                                                               tc::pack_bf16(c2 * w, s4 * w), tc::pack_bf16(c4 * w, 0.0f)));
+                        t.st_chunk(pslot, 2 * j + h, make_uint4(tc_pack_scaled(dz, s1, w), tc_pack_scaled(c1, s2, w),
+                                                               tc_pack_scaled(c2, s4, w), tc::pack_bf16(c4 * w, 0.0f)));
                     }
                     // P0..P4 commit to their ring-slot barrier, P5 completes the accumulator
                     t.issue(ST_P0 + s, s < 5 ? 1 + ps : 0);
@@ -1113,6 +1161,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     t.ld16(c0, x);
                     if (v > 0) { t.ld16(TC_SREG + c0, s1); t.ld16(TC_SREG + 64 + c0, s2); }
                     const float* b3 = BIASP(L_MLP3) + c0;
+#if TC_F32X2
+                    const float2 pw2 = make_float2(pw, pw);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float2 hv = __fadd2_rn(make_float2(x[i], x[i + 1]), make_float2(b3[i], b3[i + 1]));
+                        const float2 wh = __fmul2_rn(pw2, hv);
+                        const float2 a1 = __fadd2_rn(v > 0 ? make_float2(s1[i], s1[i + 1]) : make_float2(0.f, 0.f), wh);
+                        const float2 a2 = __ffma2_rn(wh, hv, v > 0 ? make_float2(s2[i], s2[i + 1]) : make_float2(0.f, 0.f));
+                        s1[i] = a1.x; s1[i + 1] = a1.y; s2[i] = a2.x; s2[i + 1] = a2.y;
+                    }
+#else
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float hv = x[i] + b3[i];
@@ -1120,6 +1179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         s1[i] = (v > 0 ? s1[i] : 0.0f) + wh;
                         s2[i] = fmaf(wh, hv, v > 0 ? s2[i] : 0.0f);
                     }
+#endif
                     t.st16(TC_SREG + c0, s1);
                     t.st16(TC_SREG + 64 + c0, s2);
                 }

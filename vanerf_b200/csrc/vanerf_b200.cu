@@ -6,7 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "bvh.h"
+#include "bvh_build.cuh"
 #include "rays.cuh"
 #include "geom.cuh"
 #include "frame.cuh"
@@ -46,7 +46,7 @@ struct vanerf_ctx {
     TcTables h_tc;                     // host copy of the biases / small fp32 layers (weights) + camera-space keypoints (frame)
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
-    int tc_waves = 1;
+    int tc_waves = 8;
     DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
@@ -57,12 +57,20 @@ struct vanerf_ctx {
     // frame
     FrameDev fr;
     bool have_frame = false;
-    DevBuf geo0, geo1, tex, imgm, T64, T8, Ttex, vis, verts, faces, tri_nodes, tri_prims, vtx_nodes, vtx_prims,
-        kpt_cam, xyz_ndc, xy11, zbuf, tri_rec, vtx_rec, tri_node_lb;
+    DevBuf geo0, geo1, tex, imgm, T64, T8, Ttex, vis, tri_nodes, tri_prims, vtx_nodes, vtx_prims,
+        xyz_ndc, xy11, zbuf, tri_rec, vtx_rec, tri_node_lb, upload, bvh_scratch[2];
+    // pinned staging of the per-frame host inputs (vertices, faces, camera-space keypoints): two buffers + "upload done" events
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_cap[2] = {0, 0};
+    cudaEvent_t stage_ev[2];
+    bool stage_ev_ok[2] = {false, false};
+    int stage_i = 0;
     // scratch
     DevBuf rec, s_rays, s_z, s_z2, s_sdf, s_nn, s_qvis, s_rgba, s_contrib, s_valid, s_tab;
     DevBuf s_zf, s_srcmap, s_sdf_f, s_rgba_f, s_sdf_m, s_rgba_m;      // coarse reuse (vanerf_set_reuse_coarse)
+    DevBuf s_nn_f, s_qvis_f, s_nn_m, s_qvis_m;                        // geometry reuse (vanerf_set_reuse_geometry)
     bool reuse_coarse = false;
+    bool reuse_geometry = true;
     unsigned char* imp_src_map = nullptr;   // set around the importance launch of vanerf_render_rays (coarse reuse)
 };
 
@@ -121,7 +129,8 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     memset(&c->ft, 0, sizeof(c->ft));
     memset(&c->h_tc, 0, sizeof(c->h_tc));
     memset(&c->h_prog, 0, sizeof(c->h_prog));
-    if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));
+    if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));      // developer override
+    if (const char* w = getenv("VANERF_REUSE_GEOM")) c->reuse_geometry = atoi(w) != 0;                      // developer override
 #endif
     *out = c;
     return VANERF_OK;
@@ -134,11 +143,16 @@ void vanerf_ctx_destroy(vanerf_ctx* c) {
     for (DevBuf* b : tcb) if (b->p) cudaFree(b->p);
     if (c->tc_err_host) cudaFreeHost(c->tc_err_host);
 #endif
+    for (int i = 0; i < 2; ++i) {
+        if (c->stage_ev_ok[i]) { cudaEventSynchronize(c->stage_ev[i]); cudaEventDestroy(c->stage_ev[i]); }
+        if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    }
     DevBuf* all[] = {&c->wblob, &c->netdev, &c->geo0, &c->geo1, &c->tex, &c->imgm, &c->T64, &c->T8, &c->Ttex, &c->vis,
-                     &c->verts, &c->faces, &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->kpt_cam,
+                     &c->tri_nodes, &c->tri_prims, &c->vtx_nodes, &c->vtx_prims, &c->upload, &c->bvh_scratch[0], &c->bvh_scratch[1],
                      &c->xyz_ndc, &c->xy11, &c->zbuf, &c->tri_rec, &c->vtx_rec, &c->tri_node_lb, &c->rec, &c->s_rays, &c->s_z, &c->s_z2, &c->s_sdf, &c->s_nn,
                      &c->s_qvis, &c->s_rgba, &c->s_contrib, &c->s_valid, &c->s_tab,
-                     &c->s_zf, &c->s_srcmap, &c->s_sdf_f, &c->s_rgba_f, &c->s_sdf_m, &c->s_rgba_m};
+                     &c->s_zf, &c->s_srcmap, &c->s_sdf_f, &c->s_rgba_f, &c->s_sdf_m, &c->s_rgba_m,
+                     &c->s_nn_f, &c->s_qvis_f, &c->s_nn_m, &c->s_qvis_m};
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     delete c;
 }
@@ -249,90 +263,87 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
                 volatile float t = s + c;
                 kc[((size_t)v * NKPT + k) * 3 + j] = t + M[4 * j + 3];
             }
-    bvh::Tree tt, vt;
-    bvh::build_triangles(f->verts, f->faces, F, tt);
-    bvh::build_points(f->verts, Nv, vt);
-    std::vector<float> tlb;
-    bvh::triangle_node_bounds(tt, f->verts, f->faces, tlb);
-
-    // per-primitive records in leaf order (see FrameDev); b - a and c - a are rounded once, exactly like xsub
-    std::vector<float> trec((size_t)tt.prims.size() * 4 * TRI_REC_F4), vrec((size_t)vt.prims.size() * 4);
-    for (size_t i = 0; i < tt.prims.size(); ++i) {
-        const int fi = tt.prims[i];
-        const float* a = f->verts + 3 * f->faces[3 * fi];
-        const float* b = f->verts + 3 * f->faces[3 * fi + 1];
-        const float* c = f->verts + 3 * f->faces[3 * fi + 2];
-        volatile float ab[3], ac[3];
-        for (int k = 0; k < 3; ++k) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; }
-        float* r = &trec[4 * TRI_REC_F4 * i];
-        {   // lower-bound record: unit normal, centroid, radius of the circle around it (inflated: the bound must never
-            // exceed the true distance despite rounding); a degenerate triangle gets n = 0 (sphere bound)
-            double n[3] = {(double)ab[1] * ac[2] - (double)ab[2] * ac[1], (double)ab[2] * ac[0] - (double)ab[0] * ac[2],
-                           (double)ab[0] * ac[1] - (double)ab[1] * ac[0]};
-            const double nl = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-            double cen[3], rad = 0.0;
-            for (int k = 0; k < 3; ++k) cen[k] = ((double)a[k] + b[k] + c[k]) / 3.0;
-            const float* vs[3] = {a, b, c};
-            for (int q = 0; q < 3; ++q) {
-                double d2 = 0.0;
-                for (int k = 0; k < 3; ++k) d2 += (vs[q][k] - (float)cen[k]) * (double)(vs[q][k] - (float)cen[k]);
-                rad = std::max(rad, sqrt(d2));
-            }
-            for (int k = 0; k < 3; ++k) r[16 + k] = nl > 1e-20 ? (float)(n[k] / nl) : 0.0f;
-            r[19] = (float)(rad * 1.0001 + 1e-7);
-            for (int k = 0; k < 3; ++k) r[20 + k] = (float)cen[k];
-            r[23] = 0.0f;
+    // ---- host inputs -> device through context-owned pinned staging (two buffers, so that this call never has to wait
+    // for anything but the upload issued two frames ago); nothing below synchronises the stream
+    const size_t o_verts = 0, o_faces = o_verts + (((size_t)Nv * 12 + 255) & ~(size_t)255), o_kc = o_faces + (((size_t)F * 12 + 255) & ~(size_t)255);
+    const size_t up_bytes = o_kc + ((kc.size() * 4 + 255) & ~(size_t)255);
+    {
+        const int sb = ctx->stage_i ^= 1;
+        if (ctx->stage_cap[sb] < up_bytes) {
+            if (ctx->stage[sb]) { CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[sb])); CUDA_TRY(ctx, cudaFreeHost(ctx->stage[sb])); }
+            ctx->stage[sb] = nullptr; ctx->stage_cap[sb] = 0;
+            CUDA_TRY(ctx, cudaHostAlloc(&ctx->stage[sb], up_bytes, cudaHostAllocDefault));
+            ctx->stage_cap[sb] = up_bytes;
+            if (!ctx->stage_ev_ok[sb]) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->stage_ev[sb], cudaEventDisableTiming)); ctx->stage_ev_ok[sb] = true; }
+        } else {
+            CUDA_TRY(ctx, cudaEventSynchronize(ctx->stage_ev[sb]));      // upload of two frames ago (long complete)
         }
-        r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = bvh::as_float(fi);
-        r[4] = b[0]; r[5] = b[1]; r[6] = b[2]; r[7] = ab[0];
-        r[8] = c[0]; r[9] = c[1]; r[10] = c[2]; r[11] = ab[1];
-        r[12] = ab[2]; r[13] = ac[0]; r[14] = ac[1]; r[15] = ac[2];
+        unsigned char* h = (unsigned char*)ctx->stage[sb];
+        memcpy(h + o_verts, f->verts, (size_t)Nv * 12);
+        memcpy(h + o_faces, f->faces, (size_t)F * 12);
+        memcpy(h + o_kc, kc.data(), kc.size() * 4);
+        ENSURE(ctx, ctx->upload, up_bytes);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->upload.p, h, up_bytes, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->stage_ev[sb], stream));
     }
-    for (size_t i = 0; i < vt.prims.size(); ++i) {
-        const int vi = vt.prims[i];
-        float* r = &vrec[4 * i];
-        r[0] = f->verts[3 * vi]; r[1] = f->verts[3 * vi + 1]; r[2] = f->verts[3 * vi + 2]; r[3] = bvh::as_float(vi);
-    }
+    const float* d_verts = (const float*)((unsigned char*)ctx->upload.p + o_verts);
+    const int* d_faces = (const int*)((unsigned char*)ctx->upload.p + o_faces);
 
     const size_t g0n = (size_t)V * 64 * fr.g0h * fr.g0w, g1n = (size_t)V * 8 * fr.g1h * fr.g1w, txn = (size_t)V * 8 * fr.th * fr.tw;
     ENSURE(ctx, ctx->geo0, g0n * 4); ENSURE(ctx, ctx->geo1, g1n * 4); ENSURE(ctx, ctx->tex, txn * 4);
     ENSURE(ctx, ctx->imgm, (size_t)V * H * W * 16);
     ENSURE(ctx, ctx->T64, (size_t)V * Nv * 64 * 4); ENSURE(ctx, ctx->T8, (size_t)V * Nv * 8 * 4); ENSURE(ctx, ctx->Ttex, (size_t)V * Nv * 32 * 4);
     ENSURE(ctx, ctx->vis, (size_t)V * Nv * 4);
-    ENSURE(ctx, ctx->verts, (size_t)Nv * 12); ENSURE(ctx, ctx->faces, (size_t)F * 12);
-    ENSURE(ctx, ctx->tri_nodes, tt.nodes.size() * 4); ENSURE(ctx, ctx->tri_prims, tt.prims.size() * 4);
-    ENSURE(ctx, ctx->vtx_nodes, vt.nodes.size() * 4); ENSURE(ctx, ctx->vtx_prims, vt.prims.size() * 4);
-    ENSURE(ctx, ctx->kpt_cam, kc.size() * 4);
-    ENSURE(ctx, ctx->tri_rec, trec.size() * 4); ENSURE(ctx, ctx->vtx_rec, vrec.size() * 4);
-    ENSURE(ctx, ctx->tri_node_lb, tlb.size() * 4);
+    ENSURE(ctx, ctx->tri_nodes, (size_t)BVH_MAX_NODES * 32); ENSURE(ctx, ctx->tri_prims, (size_t)F * 4);
+    ENSURE(ctx, ctx->vtx_nodes, (size_t)BVH_MAX_NODES * 32); ENSURE(ctx, ctx->vtx_prims, (size_t)Nv * 4);
+    ENSURE(ctx, ctx->tri_rec, (size_t)F * TRI_REC_F4 * 16); ENSURE(ctx, ctx->vtx_rec, (size_t)Nv * 16);
+    ENSURE(ctx, ctx->tri_node_lb, (size_t)BVH_MAX_NODES * 32);
     ENSURE(ctx, ctx->xyz_ndc, (size_t)V * Nv * 12); ENSURE(ctx, ctx->xy11, (size_t)V * Nv * 8);
     ENSURE(ctx, ctx->zbuf, (size_t)V * RASTER_S * RASTER_S * 8);
-
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->verts.p, f->verts, (size_t)Nv * 12, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->faces.p, f->faces, (size_t)F * 12, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_nodes.p, tt.nodes.data(), tt.nodes.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_prims.p, tt.prims.data(), tt.prims.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_nodes.p, vt.nodes.data(), vt.nodes.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_prims.p, vt.prims.data(), vt.prims.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->kpt_cam.p, kc.data(), kc.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_rec.p, trec.data(), trec.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->vtx_rec.p, vrec.data(), vrec.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tri_node_lb.p, tlb.data(), tlb.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(stream));       // pageable host staging above goes out of scope
+    if (F > 4 * BVH_MAX_NODES || Nv > 8 * BVH_MAX_NODES) return ctx_invalid(ctx, "mesh too large for the per-frame BVH builder");
 
     fr.geo0 = (const float*)ctx->geo0.p; fr.geo1 = (const float*)ctx->geo1.p; fr.tex = (const float*)ctx->tex.p;
     fr.imgm = (const float*)ctx->imgm.p;
     fr.T64 = (const float*)ctx->T64.p; fr.T8 = (const float*)ctx->T8.p; fr.Ttex = (const float*)ctx->Ttex.p;
     fr.vis = (const float*)ctx->vis.p;
-    fr.verts = (const float*)ctx->verts.p; fr.faces = (const int*)ctx->faces.p;
+    fr.verts = d_verts; fr.faces = d_faces;
     fr.tri_nodes = (const float4*)ctx->tri_nodes.p; fr.tri_prims = (const int*)ctx->tri_prims.p;
     fr.tri_node_lb = (const float4*)ctx->tri_node_lb.p;
     fr.vtx_nodes = (const float4*)ctx->vtx_nodes.p; fr.vtx_prims = (const int*)ctx->vtx_prims.p;
-    fr.kpt_cam = (const float*)ctx->kpt_cam.p;
+    fr.kpt_cam = (const float*)((unsigned char*)ctx->upload.p + o_kc);
     fr.tri_rec = (const float4*)ctx->tri_rec.p; fr.vtx_rec = (const float4*)ctx->vtx_rec.p;
 
     const int T = 256;
     TimedScope ts(ctx, KCL_SETUP, stream);
+    {   // acceleration structures, built on the device (bvh_build.cuh): triangle tree (leaves of 8) and vertex tree (leaves of 16)
+        // in one two-CTA launch, then leaf records and per-node slab bounds
+        const int np[2] = {F, Nv};
+        BvhBuildArgs ba[2];
+        for (int t = 0; t < 2; ++t) {
+            const size_t n = (size_t)np[t];
+            const size_t bytes = n * (6 + 3 + 1 + 3) * 4 + (size_t)BVH_MAX_NODES * (12 + 1 + 2) * 4 + (size_t)BVH_MAX_NODES * 8 + 256;
+            ENSURE(ctx, ctx->bvh_scratch[t], bytes);
+            unsigned char* q = (unsigned char*)ctx->bvh_scratch[t].p;
+            BvhBuildArgs& a = ba[t];
+            a.verts = d_verts; a.faces = t == 0 ? d_faces : nullptr; a.n = np[t];
+            a.nodes = (float4*)(t == 0 ? ctx->tri_nodes.p : ctx->vtx_nodes.p);
+            a.prims = (int*)(t == 0 ? ctx->tri_prims.p : ctx->vtx_prims.p);
+            a.node_range = (int2*)q; q += (size_t)BVH_MAX_NODES * 8;
+            a.box = (float*)q; q += n * 24; a.cen = (float*)q; q += n * 12; a.key = (float*)q; q += n * 4;
+            a.prim_b = (int*)q; q += n * 4; a.node_a = (int*)q; q += n * 4; a.node_b = (int*)q; q += n * 4;
+            a.nb = (int*)q; q += (size_t)BVH_MAX_NODES * 48; a.axis = (int*)q; q += (size_t)BVH_MAX_NODES * 4;
+            a.active = (int*)q; q += (size_t)BVH_MAX_NODES * 8;
+            a.n_nodes = (int*)q;
+        }
+        // leaf sizes from sweeps on B200 (2/4/8/16 triangles with the per-triangle lower bound x 4/8/16 vertices)
+        ba[0].leaf = 8; ba[1].leaf = 16;
+        if (const char* e = getenv("VANERF_TRI_LEAF")) ba[0].leaf = std::max(1, std::min(32, atoi(e)));       // developer override
+        VANERF_LAUNCH(k_bvh_build, 2, BVH_BUILD_THREADS, 0, stream, ba[0], ba[1]); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_tri_records, cdiv(F, 128), 128, 0, stream, d_verts, d_faces, (const int*)ctx->tri_prims.p, F, (float4*)ctx->tri_rec.p); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_vtx_records, cdiv(Nv, 128), 128, 0, stream, d_verts, (const int*)ctx->vtx_prims.p, Nv, (float4*)ctx->vtx_rec.p); CHECK_LAUNCH(ctx);
+        VANERF_LAUNCH(k_tri_node_bounds, cdiv(BVH_MAX_NODES * 32, 128), 128, 0, stream, d_verts, d_faces, (const int*)ctx->tri_prims.p,
+                      (const int2*)ba[0].node_range, (const int*)ba[0].n_nodes, (float4*)ctx->tri_node_lb.p); CHECK_LAUNCH(ctx);
+    }
     VANERF_LAUNCH(k_repack_nhwc, cdiv(g0n, T), T, 0, stream, f->feat_geo0, (float*)ctx->geo0.p, V, 64, fr.g0h, fr.g0w); CHECK_LAUNCH(ctx);
     VANERF_LAUNCH(k_repack_nhwc, cdiv(g1n, T), T, 0, stream, f->feat_geo1, (float*)ctx->geo1.p, V, 8, fr.g1h, fr.g1w); CHECK_LAUNCH(ctx);
     VANERF_LAUNCH(k_repack_nhwc, cdiv(txn, T), T, 0, stream, f->feat_tex, (float*)ctx->tex.p, V, 8, fr.th, fr.tw); CHECK_LAUNCH(ctx);
@@ -430,7 +441,8 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
                  e[0], e[2], e[3], e[4], e[5], e[6]);
         return VANERF_ERR_CUDA;
     }
-    // tiles per launch: `tc_waves` tile pairs per CTA (VANERF_TC_WAVES, default 1 = the chunk's operand images stay in L2)
+    // tiles per launch: `tc_waves` tile pairs per CTA (default 8: ~580 MB of operand images per launch at V = 3; one pair per
+    // CTA keeps the images L2 resident but costs eight times the launches, and the gather runs 20 % faster on the larger grid)
     const int max_tiles = TC_TILES * ctx->sm_count * ctx->tc_waves;
     const long long chunk = (long long)max_tiles * TC_ROWS;
     ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
@@ -743,6 +755,12 @@ int vanerf_set_reuse_coarse(vanerf_ctx* ctx, int on) {
     return VANERF_OK;
 }
 
+int vanerf_set_reuse_geometry(vanerf_ctx* ctx, int on) {
+    if (!ctx) return VANERF_ERR_INVALID;
+    ctx->reuse_geometry = on != 0;
+    return VANERF_OK;
+}
+
 // Reference calling convention of VANeRF.importance_sample (src/model.py:1425-1462): contrib_inner (R, D-2),
 // z_mid (R, D-1) -> z_fine (R, n_fine); no merge.
 int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const float* z_mid, int32_t R, int32_t D, const float* u,
@@ -823,6 +841,30 @@ int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar,
                               rgba_f, sdf_f, rc, Sc, Sf, rgba_m, sdf_m);
                 CHECK_LAUNCH(ctx);
                 if ((st = vanerf_composite(ctx, rgba_m, z2, sdf_m, rc, S2, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, nullptr, stream_))) return st;
+            } else if (ctx->reuse_geometry) {
+                // Default: the networks evaluate all S2 merged samples like the reference (src/model.py:1328-1349), but the
+                // mesh queries (cal_vis_sdf_batch / knn_points: functions of the sample position only) run for the Sf new
+                // depths only; the Sc coarse depths sit in the merged set bit for bit and keep their coarse-pass results.
+                ENSURE(ctx, ctx->s_zf, (size_t)RC * Sf * 4); ENSURE(ctx, ctx->s_srcmap, Nmax);
+                ENSURE(ctx, ctx->s_sdf_f, (size_t)RC * Sf * 4); ENSURE(ctx, ctx->s_nn_f, (size_t)RC * Sf * 4);
+                ENSURE(ctx, ctx->s_qvis_f, (size_t)RC * Sf * V);
+                ENSURE(ctx, ctx->s_sdf_m, Nmax * 4); ENSURE(ctx, ctx->s_nn_m, Nmax * 4); ENSURE(ctx, ctx->s_qvis_m, Nmax * V);
+                float* zf = (float*)ctx->s_zf.p; float* sdf_f = (float*)ctx->s_sdf_f.p; int* nn_f = (int*)ctx->s_nn_f.p;
+                unsigned char* qv_f = (unsigned char*)ctx->s_qvis_f.p;
+                float* sdf_m = (float*)ctx->s_sdf_m.p; int* nn_m = (int*)ctx->s_nn_m.p; unsigned char* qv_m = (unsigned char*)ctx->s_qvis_m.p;
+                ctx->imp_src_map = (unsigned char*)ctx->s_srcmap.p;
+                st = vanerf_importance(ctx, contrib, z, rc, Sc, utab, Sf, 0, zf, z2, stream_);
+                ctx->imp_src_map = nullptr;
+                if (st) return st;
+                if ((st = vanerf_geom_query(ctx, tar, rays, zf, rc, Sf, nullptr, sdf_f, nullptr, nn_f, qv_f, stream_))) return st;
+                {
+                    TimedScope ts(ctx, KCL_GEOM, stream);
+                    VANERF_LAUNCH(k_merge_geom, cdiv((long long)rc * S2, 256), 256, 0, stream, (const unsigned char*)ctx->s_srcmap.p, sdf, nn, qv,
+                                  sdf_f, nn_f, qv_f, rc, Sc, Sf, V, sdf_m, nn_m, qv_m);
+                    CHECK_LAUNCH(ctx);
+                }
+                if ((st = shade_impl(ctx, precision, td, rays, z2, rc, S2, sdf_m, nn_m, qv_m, rgba, nullptr, nullptr, nullptr, stream))) return st;
+                if ((st = vanerf_composite(ctx, rgba, z2, sdf_m, rc, S2, pl, pl + 3 * (size_t)RC, pl + 4 * (size_t)RC, pl + 5 * (size_t)RC, nullptr, stream_))) return st;
             } else {
             if ((st = vanerf_importance(ctx, contrib, z, rc, Sc, utab, Sf, 0, nullptr, z2, stream_))) return st;
             if ((st = vanerf_geom_query(ctx, tar, rays, z2, rc, S2, nullptr, sdf, nullptr, nn, qv, stream_))) return st;

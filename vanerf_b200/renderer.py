@@ -318,6 +318,11 @@ class Renderer:
         fewer network evaluations per ray at 64 + 64; include/vanerf_b200.h: vanerf_set_reuse_coarse).  Default off."""
         self.lib.check(self.ctx, self.lib.dll.vanerf_set_reuse_coarse(self.ctx, int(bool(on))), "vanerf_set_reuse_coarse")
 
+    def set_reuse_geometry(self, on: bool):
+        """Fine pass queries the mesh for the new depths only (default on; identical bits, the networks still evaluate every
+        merged sample; include/vanerf_b200.h: vanerf_set_reuse_geometry)."""
+        self.lib.check(self.ctx, self.lib.dll.vanerf_set_reuse_geometry(self.ctx, int(bool(on))), "vanerf_set_reuse_geometry")
+
     def render_rays(self, tar, pix_xy, n_coarse=64, n_fine=64, fine=True, precision=L.FP32):
         """One call for a ray batch: coarse pass, importance sampling, fine pass (src/model.py:1103-1360).
         Returns (R,8) rows [r,g,b,depth,alpha,sdf,0,0] for the coarse and the fine pass."""
