@@ -9,8 +9,13 @@
  *   - plain C types only; no torch types cross the boundary.
  *   - "dev" pointers are device pointers owned by the caller (e.g. the PyTorch caching allocator), "host" pointers
  *     are host memory read synchronously during the call.
- *   - every call enqueues its work on `stream` (a cudaStream_t passed as void*) and returns without synchronising;
- *     the context owns only packed weights, per-frame acceleration structures and scratch.
+ *   - every call enqueues its work on `stream` (a cudaStream_t passed as void*) and returns without synchronising the
+ *     stream, except vanerf_load_weights (packs from host memory once per model), vanerf_timing_read, vanerf_tc_check,
+ *     vanerf_tc_selftest and vanerf_tc_mma_probe, which say so.  vanerf_frame_setup stages its host inputs in pinned
+ *     buffers owned by the context (it waits at most for the upload it issued two frames earlier).  A context grows its
+ *     scratch with cudaMalloc on first use / on larger sizes.
+ *   - the context owns only packed weights, per-frame acceleration structures, staging and scratch; it holds no
+ *     process-global mutable state, and every entry point runs on the context's device and restores the caller's.
  *   - return value: 0 on success, a negative vanerf_status otherwise; no exceptions cross the ABI.
  *   - one vanerf_ctx per device per process; calls on a context are ordered by the stream.
  *   - sample index is the fastest dimension of every (ray, sample) array, as in the reference
@@ -26,7 +31,10 @@
 extern "C" {
 #endif
 
-#define VANERF_MAX_VIEWS 4
+#define VANERF_MAX_VIEWS 4       /* source views of the fp32 path */
+#define VANERF_MAX_VIEWS_BF16 3  /* source views of the bf16 tensor-core path (TMEM column budget of the batched rendering head);
+                                    vanerf_shade / vanerf_render_rays / vanerf_query_points with VANERF_BF16 and more views
+                                    return VANERF_ERR_UNSUPPORTED, nothing is truncated silently */
 #define VANERF_N_KPT 42          /* configs/vanerf.json: sp_args.n_kpt */
 #define VANERF_N_VERT 1558       /* 2 x (778 MANO + 1 seal vertex), src/networks.py:25 */
 #define VANERF_RAY_STRIDE 8      /* floats per ray record: dir.xyz, near, far, hit, pad, pad */
@@ -202,6 +210,10 @@ int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const flo
                             int32_t n_samples, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba,
                             uint8_t* valid, float* raw_out, float* latent, void* stream);
 int vanerf_tc_error(vanerf_ctx* ctx);
+/* Completion check of the bf16 path (a SYNCHRONISING call): waits for `stream`, then returns VANERF_ERR_CUDA and clears the
+ * record if a tensor-core launch since the last check gave up on a bounded wait (its results are invalid), VANERF_OK
+ * otherwise.  Without it the condition is reported by the next bf16 call on the context. */
+int vanerf_tc_check(vanerf_ctx* ctx, void* stream);
 /* Developer aid: cycle trace (tag, clock64) pairs of CTA 0 / thread 0 of the following tensor-core launches into
  * buf dev (capacity, 2) int64; buf == NULL switches the trace off and returns the number of pairs recorded. */
 int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity);

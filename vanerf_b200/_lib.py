@@ -75,6 +75,7 @@ PROTOTYPES = {
     "vanerf_launch_count": (_I64, [_P]),
     "vanerf_shade_debug_bf16": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vanerf_tc_error": (C.c_int, [_P]),
+    "vanerf_tc_check": (C.c_int, [_P, _P]),
     "vanerf_tc_profile": (C.c_int, [_P, _P, _I]),
     "vanerf_tc_selftest": (C.c_int, [_P, _P, _P, _I, _I, _P, _P]),
     "vanerf_tc_mma_probe": (C.c_int, [_P, _I, _I, _I, _I, _I, _P]),

@@ -3,7 +3,7 @@
 // Spelling of the PTX follows the CUTLASS 4.x sm100 headers (cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp,
 // tmem_allocator_sm100.hpp, cutlass/arch/barrier.h); nothing here depends on CUTLASS.
 //
-// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_TRIES tries raises the CTA-wide abort flag,
+// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_BUDGET_NS of wall time raises the CTA-wide abort flag,
 // after which all waits fall through, the kernel drains (garbage results), frees TMEM and the host reports an error.
 // A protocol bug therefore costs a wrong answer and an error code, never a hung GPU.
 #pragma once
@@ -29,7 +29,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // One try_wait: suspends the warp in hardware until the phase completes or the suspend-time hint (ns) runs out, so a
 // waiting warp does not burn issue slots polling.
 #define TC_WAIT_HINT_NS 20000u
-#define TC_WAIT_TRIES 20000               // x hint = 0.4 s when the hint is honoured in full
+#define TC_WAIT_BUDGET_NS 2000000000ull   // a wait gives up after 2 s of wall time (globaltimer), however the suspend hint is honoured
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -41,16 +41,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Returns false when the wait was abandoned (try budget spent, or the abort flag raised by another thread).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Returns false when the wait was abandoned (time budget spent, or the abort flag raised by another thread).
 // abort_flag[0] = code of the first wait that gave up, abort_flag[1 + code / 100] = last code of each wait class that
-// was still pending.  No clock and no call: the bound is a try count, so a wait site costs one loop counter.
+// was still pending.  The clock is only read after a try has failed (a try suspends the warp for up to the hint), i.e. off
+// the fast path; the bound is wall time, so time slicing, MPS or a debugger stretching the tries cannot trip it early.
 // (Measured: pure polling with mbarrier.test_wait instead of the suspending try_wait changes nothing, and moving the
 // retry loop out of line does not pay either.)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
+    unsigned long long t0 = 0;
 #pragma unroll 1
-    for (int it = 0; it < TC_WAIT_TRIES; ++it) {
+    for (;;) {
         if (mbar_try_wait(bar, parity)) return true;
         if (*abort_flag) break;           // only reached when a try timed out (>= the hint), i.e. off the fast path
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > TC_WAIT_BUDGET_NS) break;
     }
     if (*abort_flag == 0) *abort_flag = code;
     abort_flag[1 + code / 100] = code;

@@ -78,6 +78,14 @@ static int ctx_fail(vanerf_ctx* ctx, cudaError_t e, const char* what, int line) 
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "CUDA error %d (%s) at %s [vanerf_b200.cu:%d]", (int)e, cudaGetErrorString(e), what, line);
     return VANERF_ERR_CUDA;
 }
+static int ctx_state(vanerf_ctx* ctx) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "call order violated: load weights, then frame_setup, then render");
+    return VANERF_ERR_STATE;
+}
+static int ctx_unsupported(vanerf_ctx* ctx, const char* msg) {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), "unsupported: %s", msg);
+    return VANERF_ERR_UNSUPPORTED;
+}
 static int ctx_invalid(vanerf_ctx* ctx, const char* msg) {
     if (ctx) snprintf(ctx->err, sizeof(ctx->err), "invalid argument: %s", msg);
     return VANERF_ERR_INVALID;
@@ -110,18 +118,34 @@ struct TimedScope {
 #endif
 };
 
+// Every entry point that touches the device runs with the context's device current and restores the caller's.
+struct DeviceGuard {
+    int prev = -1; bool sw = false;
+    explicit DeviceGuard(const vanerf_ctx* c) {
+        if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) sw = cudaSetDevice(c->device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (sw) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
 int vanerf_ctx_create(vanerf_ctx** out, int device) {
     if (!out) return VANERF_ERR_INVALID;
     vanerf_ctx* c = new vanerf_ctx();
     c->device = device;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};      // the caller's current device is kept
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
     int sm = 0;
     if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
     c->sm_count = sm;
     memset(&c->fr, 0, sizeof(c->fr));
     memset(&c->h_net, 0, sizeof(c->h_net));
+    // opt-in shared-memory sizes are per device: set here, on this context's device (a second context on another GPU of
+    // the same process sets them again for its own device)
+    if (cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(mlp_simt_smem_floats(MAXV) * sizeof(float)) + 1024) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
 #ifndef VANERF_HOST_EMUL
     if (cudaHostAlloc((void**)&c->tc_err_host, 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&c->tc_err_dev, c->tc_err_host, 0) != cudaSuccess) { delete c; return VANERF_ERR_CUDA; }
@@ -129,6 +153,11 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     memset(&c->ft, 0, sizeof(c->ft));
     memset(&c->h_tc, 0, sizeof(c->h_tc));
     memset(&c->h_prog, 0, sizeof(c->h_prog));
+    if (cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TC_SLOT + 1024) != cudaSuccess) {
+        cudaFreeHost(c->tc_err_host); delete c; return VANERF_ERR_CUDA;
+    }
     if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));      // developer override
     if (const char* w = getenv("VANERF_REUSE_GEOM")) c->reuse_geometry = atoi(w) != 0;                      // developer override
 #endif
@@ -138,6 +167,7 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
 
 void vanerf_ctx_destroy(vanerf_ctx* c) {
     if (!c) return;
+    DeviceGuard dg_(c);
 #ifndef VANERF_HOST_EMUL
     DevBuf* tcb[] = {&c->tcw, &c->tctab, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux};
     for (DevBuf* b : tcb) if (b->p) cudaFree(b->p);
@@ -173,6 +203,7 @@ int64_t vanerf_launch_count(const vanerf_ctx* c) { return c ? c->launches : 0; }
 
 // ------------------------------------------------------------------------------------------------ weights
 int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !w) return VANERF_ERR_INVALID;
     const vanerf_linear* src[L_COUNT] = {
         &w->geo_at[0], &w->geo_at[1], &w->geo_f[0], &w->geo_f[1], &w->geo8_at[0], &w->geo8_at[1], &w->geo8_f[0], &w->geo8_f[1],
@@ -235,6 +266,7 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
 
 // ------------------------------------------------------------------------------------------------ frame
 int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_out, void* stream_) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !f) return VANERF_ERR_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int V = f->n_views, H = f->height, W = f->width, Nv = f->n_verts, F = f->n_faces;
@@ -397,6 +429,7 @@ static TargetDev make_target(const vanerf_target* t) {
 
 int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t R, const float* ztab,
                        int32_t S, float* rays, float* z, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar || !pix_xy || !ztab || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_sample_rays");
     TimedScope ts(ctx, KCL_RAYS, (cudaStream_t)stream);
     VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ztab, S, rays, z);
@@ -406,8 +439,9 @@ int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t*
 
 int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
                       float* pts, float* sdf, int32_t* face, int32_t* nn_vert, uint8_t* qvis, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_geom_query");
-    if (!ctx->have_frame) return VANERF_ERR_STATE;
+    if (!ctx->have_frame) return ctx_state(ctx);
     TimedScope ts(ctx, KCL_GEOM, (cudaStream_t)stream);
     // ray batches: one warp per (block of 32 rays, depth index), see GEOM_RAY_LANES in geom.cuh
 #if GEOM_RAY_LANES
@@ -425,6 +459,16 @@ int vanerf_geom_query(vanerf_ctx* ctx, const vanerf_target* tar, const float* ra
 }
 
 #ifndef VANERF_HOST_EMUL
+// Reports (and clears) the abort record of the tensor-core kernels: a bounded mbarrier wait that gave up made its launch
+// drain with garbage results instead of hanging the GPU.  The record is written through mapped host memory.
+static bool tc_take_error(vanerf_ctx* ctx) {
+    volatile int* e = ctx->tc_err_host;
+    if (!e[0]) return false;
+    snprintf(ctx->err, sizeof(ctx->err), "tensor-core kernel: a bounded wait gave up (code %d; pending issue %d acc %d producer %d rec %d pe %d); "
+             "the results of that call are invalid", e[0], e[2], e[3], e[4], e[5], e[6]);
+    for (int i = 0; i < 8; ++i) e[i] = 0;
+    return true;
+}
 // Tensor-core shading: gather (bf16 operand images) + fused MLP per chunk of 2 x SM-count tiles of 128 samples, so that
 // one chunk's images (<= 75 MB at V = 3) stay L2 resident between the two kernels.
 static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, const float* z, int S, long long N, const float* sdf,
@@ -435,23 +479,13 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         snprintf(ctx->err, sizeof(ctx->err), "bf16 tensor-core path supports up to %d source views (got %d)", TC_MAXV, V);
         return VANERF_ERR_UNSUPPORTED;
     }
-    if (*ctx->tc_err_host) {
-        const int* e = ctx->tc_err_host;
-        snprintf(ctx->err, sizeof(ctx->err), "tensor-core kernel: a bounded wait gave up earlier (code %d; pending issue %d acc %d producer %d rec %d pe %d)",
-                 e[0], e[2], e[3], e[4], e[5], e[6]);
-        return VANERF_ERR_CUDA;
-    }
+    if (tc_take_error(ctx)) return VANERF_ERR_CUDA;        // an earlier launch gave up: reported once, then the path is usable again
     // tiles per launch: `tc_waves` tile pairs per CTA (default 8: ~580 MB of operand images per launch at V = 3; one pair per
     // CTA keeps the images L2 resident but costs eight times the launches, and the gather runs 20 % faster on the larger grid)
     const int max_tiles = TC_TILES * ctx->sm_count * ctx->tc_waves;
     const long long chunk = (long long)max_tiles * TC_ROWS;
     ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
     ENSURE(ctx, ctx->tc_aux, (size_t)max_tiles * TC_ROWS * V * TC_AUX_BYTES);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        attr_set = true;
-    }
     if (!tc_program_matches(ctx->h_prog)) {           // the kernels execute the compile-time copy (kProg)
         snprintf(ctx->err, sizeof(ctx->err), "tensor-core path: packing script and compiled MMA program disagree");
         return VANERF_ERR_STATE;
@@ -509,12 +543,6 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
     const int chunk = (int)(N < SHADE_CHUNK ? N : SHADE_CHUNK);
     ENSURE(ctx, ctx->rec, (size_t)chunk * V * REC_STRIDE * 4);
     const size_t smem = mlp_simt_smem_floats(V) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)(mlp_simt_smem_floats(MAXV) * sizeof(float)) + 1024));
-        attr_set = true;
-    }
     for (long long s0 = 0; s0 < N; s0 += chunk) {
         const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
         const int gblocks = min(cdiv(nc, GATHER_THREADS / 16), ctx->sm_count * 8);
@@ -536,8 +564,9 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
 int vanerf_shade(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* rays, const float* z, int32_t R,
                  int32_t S, const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
                  float* raw_out, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar || !rays || !z || !sdf || !nn_vert || !qvis || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_shade");
-    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (!ctx->have_frame || !ctx->have_weights) return ctx_state(ctx);
     if (precision != VANERF_FP32 && precision != VANERF_BF16) return ctx_invalid(ctx, "precision");
     return shade_impl(ctx, precision, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, nullptr,
                       (cudaStream_t)stream);
@@ -547,8 +576,9 @@ int vanerf_shade(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const
 int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
                        const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
                        float* raw_out, float* latent, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar) return VANERF_ERR_INVALID;
-    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (!ctx->have_frame || !ctx->have_weights) return ctx_state(ctx);
     return shade_impl(ctx, VANERF_FP32, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
                       (cudaStream_t)stream);
 }
@@ -558,14 +588,16 @@ int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* r
 int vanerf_shade_debug_bf16(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
                             const float* sdf, const int32_t* nn_vert, const uint8_t* qvis, float* rgba, uint8_t* valid,
                             float* raw_out, float* latent, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar) return VANERF_ERR_INVALID;
-    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (!ctx->have_frame || !ctx->have_weights) return ctx_state(ctx);
     return shade_impl(ctx, VANERF_BF16, make_target(tar), rays, z, R, S, sdf, nn_vert, qvis, rgba, valid, raw_out, latent,
                       (cudaStream_t)stream);
 }
 // Cycle trace of CTA 0 / thread 0 of the next k_mlp_tc launches: buf dev (capacity, 2) int64 pairs (tag, clock64), NULL = off.
 // Returns the number of pairs recorded so far (after a stream synchronise) when buf == NULL.
 int vanerf_tc_profile(vanerf_ctx* ctx, long long* buf, int32_t capacity) {
+    DeviceGuard dg_(ctx);
 #if !defined(VANERF_HOST_EMUL) && defined(VANERF_TC_TRACE)
     if (!ctx) return VANERF_ERR_INVALID;
     int n = 0, zero = 0;
@@ -590,32 +622,42 @@ int vanerf_tc_error(vanerf_ctx* ctx) {
     return 0;
 #endif
 }
+// Completion check of the bf16 path: synchronises `stream`, then returns VANERF_ERR_CUDA (message in vanerf_last_error) and
+// clears the record if any tensor-core launch since the last check gave up; VANERF_OK otherwise.
+int vanerf_tc_check(vanerf_ctx* ctx, void* stream) {
+    if (!ctx) return VANERF_ERR_INVALID;
+    DeviceGuard dg_(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+#ifndef VANERF_HOST_EMUL
+    if (tc_take_error(ctx)) return VANERF_ERR_CUDA;
+#endif
+    return VANERF_OK;
+}
 // D (128, Npad) = bf16(A (128, K) dev) x bf16(W (N, K) host)^T through one tcgen05 step; K % 16 == 0, K <= 256, N <= 128
 int vanerf_tc_selftest(vanerf_ctx* ctx, const float* A_dev, const float* W_host, int32_t K, int32_t N, float* D_dev, void* stream_) {
+    DeviceGuard dg_(ctx);
 #ifndef VANERF_HOST_EMUL
     if (!ctx || !A_dev || !W_host || !D_dev || K <= 0 || K > 256 || (K & 15) || N <= 0 || N > 128) return ctx_invalid(ctx, "vanerf_tc_selftest");
     cudaStream_t stream = (cudaStream_t)stream_;
-    static TcProg P;
-    static TcTables T;                 // biases etc. are not used by the self test
+    std::vector<TcProg> Pv(1);         // one-step program of this test (heap: the structs are several KB)
+    std::vector<TcTables> Tv(1);       // biases etc. are not used by the self test
+    memset(&Tv[0], 0, sizeof(TcTables));
+    TcProg& P = Pv[0];
     std::vector<uint16_t> img;
     tc_build_single(W_host, N, K, P, img);
-    DevBuf blob, tab;
+    struct Tmp { DevBuf b; ~Tmp() { if (b.p) cudaFree(b.p); } } blob_, tab_;     // freed on every return path
+    DevBuf& blob = blob_.b; DevBuf& tab = tab_.b;
     ENSURE(ctx, blob, img.size() * 2);
     ENSURE(ctx, tab, sizeof(TcTables));
-    CUDA_TRY(ctx, cudaMemcpyAsync(tab.p, &T, sizeof(TcTables), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tab.p, &Tv[0], sizeof(TcTables), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(blob.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_prog, &P, sizeof(TcProg), 0, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUDA_TRY(ctx, cudaStreamSynchronize(stream));          // the host copies above go out of scope with this call
     VANERF_LAUNCH(k_tc_selftest, 1, TC_THREADS, TC_SMEM_BYTES, stream, (const TcTables*)tab.p, (const unsigned char*)blob.p, A_dev, K,
                   (N + 15) & ~15, D_dev, ctx->tc_err_dev);
     CHECK_LAUNCH(ctx);
     CUDA_TRY(ctx, cudaStreamSynchronize(stream));
-    cudaFree(blob.p); cudaFree(tab.p);
-    if (*ctx->tc_err_host) {
-        snprintf(ctx->err, sizeof(ctx->err), "tensor-core self test: bounded wait gave up (code %d)", *ctx->tc_err_host);
-        *ctx->tc_err_host = 0;
-        return VANERF_ERR_CUDA;
-    }
+    if (tc_take_error(ctx)) return VANERF_ERR_CUDA;
     return VANERF_OK;
 #else
     (void)A_dev; (void)W_host; (void)K; (void)N; (void)D_dev; (void)stream_;
@@ -653,17 +695,17 @@ int vanerf_tc_program_check(void) {
 // Developer measurement: pacing of small tcgen05.mma (see k_tc_mma_probe).  out_host: (2 warps, 2) cycles of CTA 0
 // [issue, issue + completion]; n_ctas CTAs run the same stream concurrently.
 int vanerf_tc_mma_probe(vanerf_ctx* ctx, int32_t n, int32_t reps, int32_t n_acc, int32_t mode, int32_t n_ctas, long long* out_host) {
+    DeviceGuard dg_(ctx);
 #ifndef VANERF_HOST_EMUL
     if (!ctx || !out_host || n < 16 || n > 256 || (n & 15) || reps <= 0 || n_acc <= 0 || n_acc * n > 256 || n_ctas <= 0) return ctx_invalid(ctx, "vanerf_tc_mma_probe");
     long long* d = nullptr;
     CUDA_TRY(ctx, cudaMalloc(&d, (size_t)n_ctas * 4 * sizeof(long long)));
+    struct Free { long long* p; ~Free() { cudaFree(p); } } free_d{d};
     CUDA_TRY(ctx, cudaMemset(d, 0, (size_t)n_ctas * 4 * sizeof(long long)));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k_tc_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TC_SLOT + 1024));
     k_tc_mma_probe<<<n_ctas, 128, 6 * TC_SLOT + 1024>>>(n, reps, n_acc, mode, d);
     CHECK_LAUNCH(ctx);
     CUDA_TRY(ctx, cudaDeviceSynchronize());
     CUDA_TRY(ctx, cudaMemcpy(out_host, d, 4 * sizeof(long long), cudaMemcpyDeviceToHost));
-    cudaFree(d);
     return VANERF_OK;
 #else
     (void)n; (void)reps; (void)n_acc; (void)mode; (void)n_ctas; (void)out_host;
@@ -675,8 +717,10 @@ int vanerf_tc_mma_probe(vanerf_ctx* ctx, int32_t n, int32_t reps, int32_t n_acc,
 int vanerf_query_points(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* pts, const float* view,
                         int32_t N, const float* sdf_in, const uint8_t* qvis_in, float* raw_out, uint8_t* valid, float* rgba,
                         void* stream_) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar || !pts || !view || N <= 0) return ctx_invalid(ctx, "vanerf_query_points");
-    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (!ctx->have_frame || !ctx->have_weights) return ctx_state(ctx);
+    if (precision != VANERF_FP32 && precision != VANERF_BF16) return ctx_invalid(ctx, "precision");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int V = ctx->fr.V;
     ENSURE(ctx, ctx->s_sdf, (size_t)N * 4);
@@ -704,18 +748,21 @@ int vanerf_timing_enable(vanerf_ctx* ctx, int on) {
 // Synchronises the recorded events and accumulates; ms_out / count_out have 7 entries:
 // setup, rays, geom, gather, mlp, composite, importance.
 int vanerf_timing_read(vanerf_ctx* ctx, double* ms_out, int64_t* count_out, int reset) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !ms_out || !count_out) return VANERF_ERR_INVALID;
 #ifndef VANERF_HOST_EMUL
+    cudaError_t first = cudaSuccess;
     for (auto& e : ctx->evs) {
-        CUDA_TRY(ctx, cudaEventSynchronize(e.b));
         float ms = 0.f;
-        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e.a, e.b));
-        ctx->t_ms[e.kc] += ms;
-        ctx->t_cnt[e.kc] += 1;
+        cudaError_t rc = cudaEventSynchronize(e.b);
+        if (rc == cudaSuccess) rc = cudaEventElapsedTime(&ms, e.a, e.b);
+        if (rc == cudaSuccess) { ctx->t_ms[e.kc] += ms; ctx->t_cnt[e.kc] += 1; }
+        else if (first == cudaSuccess) first = rc;
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
     ctx->evs.clear();
+    CUDA_TRY(ctx, first);
 #endif
     for (int i = 0; i < KCL_COUNT; ++i) { ms_out[i] = ctx->t_ms[i]; count_out[i] = ctx->t_cnt[i]; }
     if (reset) for (int i = 0; i < KCL_COUNT; ++i) { ctx->t_ms[i] = 0; ctx->t_cnt[i] = 0; }
@@ -724,9 +771,10 @@ int vanerf_timing_read(vanerf_ctx* ctx, double* ms_out, int64_t* count_out, int 
 
 int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t R, int32_t S,
                      float* color, float* depth, float* alpha, float* sdf_out, float* contrib, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !rgba || !z || !mesh_sdf || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_composite");
-    if (S > 32 * COMP_MAX_PER_LANE) return VANERF_ERR_UNSUPPORTED;
-    if (!ctx->have_weights) return VANERF_ERR_STATE;
+    if (S > 32 * COMP_MAX_PER_LANE) return ctx_unsupported(ctx, "vanerf_composite: too many samples per ray");
+    if (!ctx->have_weights) return ctx_state(ctx);
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
     TimedScope ts(ctx, KCL_COMPOSITE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_composite, blocks, COMP_WARPS * 32, 0, stream, rgba, z, mesh_sdf, R, S, ctx->h_net.beta, color, depth, alpha,
@@ -737,10 +785,11 @@ int vanerf_composite(vanerf_ctx* ctx, const float* rgba, const float* z, const f
 
 int vanerf_importance(vanerf_ctx* ctx, const float* contrib, const float* z, int32_t R, int32_t S, const float* u,
                       int32_t nf, int32_t u_per_ray, float* z_fine_only, float* z_out, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !contrib || !z || !u || !z_out || R <= 0 || S < 3 || nf <= 0) return ctx_invalid(ctx, "vanerf_importance");
     const float* zmid_in = nullptr;
     const size_t smem = (size_t)COMP_WARPS * (2 * (S - 1) + S + nf) * sizeof(float);
-    if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) return ctx_unsupported(ctx, "importance sampling: depths per ray exceed the shared-memory budget");
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
     TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib, z, zmid_in, R, S, u, nf, u_per_ray, z_fine_only, z_out,
@@ -765,9 +814,10 @@ int vanerf_set_reuse_geometry(vanerf_ctx* ctx, int on) {
 // z_mid (R, D-1) -> z_fine (R, n_fine); no merge.
 int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const float* z_mid, int32_t R, int32_t D, const float* u,
                           int32_t nf, int32_t u_per_ray, float* z_fine, void* stream) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !contrib_inner || !z_mid || !u || !z_fine || R <= 0 || D < 3 || nf <= 0) return ctx_invalid(ctx, "vanerf_importance_mid");
     const size_t smem = (size_t)COMP_WARPS * (2 * (D - 1) + D + nf) * sizeof(float);
-    if (smem > 48 * 1024) return VANERF_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) return ctx_unsupported(ctx, "importance sampling: depths per ray exceed the shared-memory budget");
     const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
     TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib_inner, (const float*)nullptr, z_mid, R, D, u, nf,
@@ -787,9 +837,11 @@ size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t R, int32_t S) {
 int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const int32_t* pix_xy, int32_t R,
                        int32_t Sc, int32_t Sf, int32_t fine, const float* ztab, const float* utab, float* out_coarse,
                        float* out_fine, void* stream_) {
+    DeviceGuard dg_(ctx);
     if (!ctx || !tar || !pix_xy || !ztab || !out_coarse || R <= 0 || Sc < 3) return ctx_invalid(ctx, "vanerf_render_rays");
     if (fine && (!utab || !out_fine || Sf <= 0)) return ctx_invalid(ctx, "vanerf_render_rays: fine pass needs utab/out_fine");
-    if (!ctx->have_frame || !ctx->have_weights) return VANERF_ERR_STATE;
+    if (!ctx->have_frame || !ctx->have_weights) return ctx_state(ctx);
+    if (precision != VANERF_FP32 && precision != VANERF_BF16) return ctx_invalid(ctx, "precision");
     cudaStream_t stream = (cudaStream_t)stream_;
     const TargetDev td = make_target(tar);
     const int V = ctx->fr.V;
