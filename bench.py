@@ -80,24 +80,19 @@ class ClockSampler:
 
 def ncu_traffic(precision):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture
-    (profiles/r01_<precision>_traffic.json, written by tools/ncu_key.py); None when no capture is committed."""
-    p = os.path.join(ROOT, "profiles", f"r01_{precision}_traffic.json")
-    try:
-        return json.load(open(p))["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    (profiles/r02_<precision>_traffic.json, else r01; written by tools/ncu_key.py); None when no capture is committed."""
+    for rnd in ("r02", "r01"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", f"{rnd}_{precision}_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            continue
+    return None
 
 
-def partition(rank, world):
-    """Interleaved pixel partition: G=2 -> 1x2, 4 -> 2x2, 8 -> 4x2 (y-period x x-period)."""
-    gy, gx = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (4, 2)}.get(world, (world, 1))
-    ry, rx = divmod(rank, gx)
-    ys, xs = np.meshgrid(np.arange(ry, H, gy), np.arange(rx, W, gx), indexing="ij")
-    return np.stack([xs, ys], -1).reshape(-1, 2).astype(np.int32), (gy, gx, ry, rx)
-
-
-def cpu_port_rays_per_s(n_side, fine, steps=1, warmup=0, layout="narrow"):
-    """The oracle (CPU restatement of the reference) on an n_side x n_side lattice of target pixels."""
+def cpu_port(n_side, fine, steps=1, warmup=0, layout="narrow"):
+    """The oracle (CPU restatement of the reference: oracle/oracle_torch.py + oracle/geom_oracle.c) on an n_side x n_side lattice
+    of target pixels of the 334x512 view.  Returns rays/s of the render alone, its seconds, the ray count and the seconds
+    of the per-frame setup (vertex visibility raster, vertex tables, global feature), which is timed separately."""
     import torch
     from oracle import oracle_torch as OT
     from vanerf_b200 import synthetic, weights
@@ -107,62 +102,69 @@ def cpu_port_rays_per_s(n_side, fine, steps=1, warmup=0, layout="narrow"):
     sd = weights.init_state_dict(H, W, mode="ref")
     ii, jj = np.meshgrid(np.arange(n_side), np.arange(n_side), indexing="ij")
     pix = np.stack([(5 + (W - 10) * ii // n_side).ravel(), (8 + (H - 16) * jj // n_side).ravel()], 1).astype(np.int64)
-    times = []
+    t_render, t_setup = [], []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        orc = OT.Oracle(sd, inp)                    # per-frame setup is part of a view
+        orc = OT.Oracle(sd, inp)
+        orc.frame_setup()
+        t1 = time.perf_counter()
         orc.render(fine=fine, pixels=pix, S_c=S_C, S_f=S_F)
+        t2 = time.perf_counter()
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return pix.shape[0] / float(np.mean(times)), float(np.mean(times)), pix.shape[0]
+            t_setup.append(t1 - t0)
+            t_render.append(t2 - t1)
+    sec = float(np.mean(t_render))
+    return pix.shape[0] / sec, sec, pix.shape[0], float(np.mean(t_setup))
 
 
 def run_reference(args):
+    """Reference arm: the reference's algorithm on the host cores (the oracle port: the reference itself needs /root/reference,
+    kaolin and pytorch3d, none of which exist on the GPU box).  A step = a bounded sample of the workload: 1 024 rays (32 x 32
+    lattice of the 334x512 view) x (64 coarse + 128 fine) evaluations, all host threads; the per-frame setup is timed
+    separately and NOT charged to the rays (a full view would amortise it over 171 008 rays)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    n_side = 12
-    rps, sec, n = cpu_port_rays_per_s(n_side, True, steps=max(1, args.steps), warmup=min(args.warmup, 1),
-                                      layout="bvv" if args.workload == "C" else "narrow")
-    sample = f"{n} rays ({n_side}x{n_side} lattice of the 334x512 view), 64 coarse + 128 fine evaluations/ray, V=3, per-frame setup included"
+    n_side = 32
+    rps, sec, n, setup = cpu_port(n_side, True, steps=max(1, args.steps), warmup=min(args.warmup, 1),
+                                  layout="bvv" if args.workload == "C" else "narrow")
+    sample = (f"{n} rays ({n_side}x{n_side} lattice of the 334x512 view), 64 coarse + 128 fine evaluations/ray, V=3; per-frame setup "
+              f"({setup:.2f} s) timed separately and not included")
     line = {"impl": "reference", "metric": "rays_per_s", "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(args, "cpu"),
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, "cpu"), "setup_s": setup,
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def config_dict(args, where):
-    return {"workload": f"{'C: vanerf_bvv big-view-variation' if args.workload == 'C' else 'B: vanerf.json'} full 334x512 novel view, "
+def config_dict(args, where, workload=None):
+    wl = workload or args.workload
+    return {"workload": f"{'C: vanerf_bvv big-view-variation' if wl == 'C' else 'B: vanerf.json'} full 334x512 novel view, "
                         f"171008 rays, V=3 source views, 64 coarse + 128 fine evaluations/ray (fine=True, uniform=True)",
             "precision": args.precision, "rays_per_view": H * W, "source_views": V, "samples": [S_C, S_C + S_F],
-            "ray_partition": "interleaved pixels across ranks + NCCL all_gather of output tiles" if args.gpus > 1 else "single GPU",
+            "ray_partition": "interleaved pixels across ranks (vanerf_b200.dist.render_view) + NCCL all_gather of output tiles" if args.gpus > 1 else "single GPU",
             "l2": "L2 flushed (256 MiB write) between timed iterations; per-step working set (gather records) exceeds L2",
             "where": where}
 
 
-def run_dynamic(args):
-    """Workload D (BASELINE.json configs[3], render_dynamic): a sequence of frames, each with its own mesh, source images
-    and feature maps and its own 334x512 target camera on a 360-degree path.  A step = `--frames` frames end to end
-    from pinned host buffers: H2D of the frame's maps, per-frame setup (BVH, vertex visibility, vertex tables, bf16 maps),
-    render, D2H of the image.  Frames are dealt round-robin to the ranks (vanerf_b200.dynamic), no collective inside the
-    timed path; per-GPU work shrinks with N ("strong" scaling over a fixed sequence)."""
+def dist_env():
+    return int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def measure_dynamic(args, net, F, steps, warmup):
+    """Workload D (BASELINE.json configs[3], render_dynamic): a sequence of F frames, each with its own mesh, source images
+    and feature maps and its own 334x512 target camera on a 360-degree path.  A step = all F frames end to end from pinned
+    host buffers: H2D of the frame's maps, per-frame setup (BVHs, vertex visibility, vertex tables, bf16 maps), render, D2H
+    of the image.  Frames are dealt round-robin to the ranks (vanerf_b200.dynamic), no collective inside the timed path;
+    per-GPU work shrinks with N ("strong" scaling over a fixed sequence).  Returns the result dict on rank 0."""
     import torch
     import torch.distributed as dist
-    from vanerf_b200 import dynamic, synthetic, weights
-    from vanerf_b200.model import VANeRF
-
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    F = max(args.frames, world)
+    from vanerf_b200 import dynamic, synthetic
+    world, rank, local = dist_env()
+    dev = net.device
+    F = max(F, world)
     ids = dynamic.frames_for_rank(F, rank, world)
-    net = VANeRF(device=dev, precision=args.precision).eval()
-    net.load_state_dict(weights.init_state_dict(H, W, mode="ref"))
     pin = lambda t: t.contiguous().pin_memory()
     frames = {}
     for f in ids:                                               # synthetic frames of this rank, pinned host memory
@@ -185,37 +187,55 @@ def run_dynamic(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(warmup):
         step()
     sync_all()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = net.renderer.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
         a.record()
         step()
         b.record()
     sync_all()
+    net.renderer.finish()
     t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = float(t.item()) / steps
+    if rank != 0:
+        return None
+    clk = clocks.stop()
+    rps = F * H * W / (ms_step * 1e-3)
+    return {"metric": "rays_per_s", "value": rps, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "ms_per_frame": ms_step / F, "frames": F, "frames_per_s": F / (ms_step * 1e-3), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"D: render_dynamic, {F} frames x one 334x512 view (171008 rays, V=3, 64 coarse + 128 fine "
+                                   f"evaluations/ray), per-frame mesh / maps / camera, per-frame setup included",
+                       "precision": args.precision, "frame_partition": "round robin over ranks, no collective in the path",
+                       "l2": "every frame brings new maps and records: the working set exceeds L2", "where": "gpu"},
+            "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": dynamic.h2d_bytes(frames[ids[0]]) * F, "d2h_bytes_per_step": F * 8 * H * W * 4,
+                    "note": "the timed step IS the end-to-end path (host buffers in, host images out)"},
+            "gpu_launches": int(net.renderer.launches - l0), "clocks": clk}
+
+
+def run_dynamic(args):
+    import torch
+    import torch.distributed as dist
+    from vanerf_b200 import weights
+    from vanerf_b200.model import VANeRF
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    net = VANeRF(device=dev, precision=args.precision).eval()
+    net.load_state_dict(weights.init_state_dict(H, W, mode="ref"))
+    line = measure_dynamic(args, net, args.frames, args.steps, max(1, min(args.warmup, 2)))
     if rank == 0:
-        clk = clocks.stop()
-        rps = F * H * W / (ms_step * 1e-3)
-        h2d = dynamic.h2d_bytes(frames[ids[0]]) * F
-        line = {"metric": "rays_per_s", "value": rps, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "ms_per_frame": ms_step / F, "frames_per_s": F / (ms_step * 1e-3), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": f"D: render_dynamic, {F} frames x one 334x512 view (171008 rays, V=3, 64 coarse + 128 fine "
-                                       f"evaluations/ray), per-frame mesh / maps / camera, per-frame setup included",
-                           "precision": args.precision, "frame_partition": "round robin over ranks, no collective in the path",
-                           "l2": "every frame brings new maps and records: the working set exceeds L2", "where": "gpu"},
-                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": F * 8 * H * W * 4,
-                        "note": "the timed step IS the end-to-end path (host buffers in, host images out)"},
-                "gpu_launches": int(net.renderer.launches - l0), "clocks": clk}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -228,13 +248,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    # headline = the bf16-MLP tensor-core path (north star kernel 2); the fp32 FFMA path is measured next to it
+    # headline = the bf16-MLP tensor-core path (north star kernel 2); the fp32 path is measured next to it
     ap.add_argument("--precision", default=os.environ.get("VANERF_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--workload", default="B", choices=["B", "C", "D"], help="headline workload of the JSON line (default B; C and D are "
+                    "also measured as secondary blocks of the default run)")
+    ap.add_argument("--frames", type=int, default=64, help="workload D: frames per step (BASELINE.json configs[3]: 64)")
     ap.add_argument("--no-fp32-path", action="store_true", help="skip the secondary fp32-path measurement")
-    ap.add_argument("--workload", default="B", choices=["B", "C", "D"])
-    ap.add_argument("--frames", type=int, default=8, help="workload D: frames per step (BASELINE.json configs[3] uses 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reuse-variant", action="store_true", help="skip the secondary coarse-reuse measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the workload C / D blocks (developer runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -244,136 +266,178 @@ def main():
     import torch
     import torch.distributed as dist
     from vanerf_b200 import _lib as L
+    from vanerf_b200 import dist as D
     from vanerf_b200 import synthetic, weights
     from vanerf_b200.model import VANeRF
 
     # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    rank = int(os.environ.get("RANK", 0))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    world, rank, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     W_steps = max(3, args.warmup)
     prec = L.FP32 if args.precision == "fp32" else L.BF16
-
-    sc = synthetic.make_scene(H, W, V, layout="bvv" if args.workload == "C" else "narrow")
-    inp_host = synthetic.to_torch(sc)                                   # CPU tensors, reference layouts
     sd = weights.init_state_dict(H, W, mode="ref")
     net = VANeRF(device=dev, precision=args.precision).eval()
     net.load_state_dict(sd)
     r = net.renderer
-
-    # ---------------- device-resident inputs
-    mv = lambda t: t.to(dev)
-    inp = dict(inp_host)
-    inp["img"], inp["feat_tex"], inp["src_foreground_mask"] = mv(inp_host["img"]), mv(inp_host["feat_tex"]), mv(inp_host["src_foreground_mask"])
-    inp["feat_geo"] = [mv(t) for t in inp_host["feat_geo"]]
-    r.set_frame(inp["img"], inp["cam_in"], inp["targets"], inp["sp_data"], inp["feat_geo"], inp["feat_tex"], inp["src_foreground_mask"])
-    tar = r.make_target(inp["cam_tar"], inp["bounds"])
-    pix_np, (gy, gx, ry, rx) = partition(rank, world)
-    pix = torch.from_numpy(pix_np).to(dev)
-    R_local = pix.shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    tiles = [torch.empty(R_local, 8, device=dev) for _ in range(world)] if world > 1 else None
-
-    def step_resident():
-        oc, of = r.render_rays(tar, pix, S_C, S_F, True, prec)
-        if world > 1:
-            dist.all_gather(tiles, of)
-        return of
+    R_local = D.partition_pixels(H, W, rank, world).shape[0]
+    pk = peaks()
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W_steps):
-        step_resident()
-    sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    r.timing(True)
-    r.timing_read(reset=True)
-    launches0 = r.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        step_resident()
-        b.record()
-    sync_all()
-    ms_local = sum(a.elapsed_time(b) for a, b in ev)
-    ktimes = r.timing_read(reset=True)
-    r.timing(False)
-    launches = r.launches - launches0
-    t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    value = H * W / (ms_step * 1e-3)
-
-    # ---------------- end to end through the public API, host buffers
-    pin = lambda x: x.contiguous().pin_memory()
-    h_img, h_tex, h_fg = pin(inp_host["img"]), pin(inp_host["feat_tex"]), pin(inp_host["src_foreground_mask"].to(torch.uint8))
-    h_g0, h_g1 = pin(inp_host["feat_geo"][0]), pin(inp_host["feat_geo"][1])
-    h_out = torch.empty(H * W, 8).pin_memory() if rank == 0 else None
-    h2d = sum(x.numel() * x.element_size() for x in (h_img, h_tex, h_fg, h_g0, h_g1))
-    d2h = H * W * 8 * 4
-
-    def step_e2e():
-        d_img, d_tex = h_img.to(dev, non_blocking=True), h_tex.to(dev, non_blocking=True)
-        d_fg = h_fg.to(dev, non_blocking=True).bool()
-        d_g = [h_g0.to(dev, non_blocking=True), h_g1.to(dev, non_blocking=True)]
-        out = VANeRF.batch_render_pifu_nerf(net, d_img, inp["cam_in"], inp["hand_type"], inp["targets"], V, inp["cam_tar"], 1, 0, None,
-                                            d_g, d_tex, None, inp["sp_data"], inp["objcenter"], fine=True, uniform=True,
-                                            sample_per_ray_c=S_C, sample_per_ray_f=S_F, src_foreground_mask=d_fg, bounds=inp["bounds"],
-                                            pixel_override=pix[None])
-        rows = torch.cat([out["tex_fg_fine"][0].reshape(3, -1).T, out["depth_fine"].reshape(-1, 1), out["alpha_fine"].reshape(-1, 1),
-                          out["sdf"].reshape(-1, 1), out["tex_fg"][0].reshape(3, -1).T[:, :2]], 1).contiguous()
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_gather(tiles, rows)
-            full = torch.cat(tiles, 0)
-        else:
-            full = rows
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure_view(layout, precision, steps, warmup, e2e=True):
+        """One workload (camera layout) on one precision path: (1) timed views with inputs resident, NO per-kernel events in the
+        loop; (2) a second, instrumented pass of the same views for the per-kernel-class times (roofline); (3) end to end through
+        VANeRF.batch_render_pifu_nerf with pinned host buffers.  Multi-GPU: vanerf_b200.dist.render_view (interleaved pixel
+        partition, all_gather of tiles, image assembled in the reference's pixel order on every rank)."""
+        inp_host = synthetic.to_torch(synthetic.make_scene(H, W, V, layout=layout))
+        mv = lambda t: t.to(dev)
+        inp = dict(inp_host)
+        inp["img"], inp["feat_tex"], inp["src_foreground_mask"] = mv(inp_host["img"]), mv(inp_host["feat_tex"]), mv(inp_host["src_foreground_mask"])
+        inp["feat_geo"] = [mv(t) for t in inp_host["feat_geo"]]
+        r.set_frame(inp["img"], inp["cam_in"], inp["targets"], inp["sp_data"], inp["feat_geo"], inp["feat_tex"], inp["src_foreground_mask"])
+        tar = r.make_target(inp["cam_tar"], inp["bounds"])
+        step = lambda: D.render_view(r, tar, H, W, rank, world, S_C, S_F, True, precision)
+        for _ in range(warmup):
+            step()
+        sync_all()
+        clocks = ClockSampler(local)
         if rank == 0:
-            h_out.copy_(full, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            clocks.start()
+        launches0 = r.launches
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        sync_all()
+        r.finish()
+        launches = r.launches - launches0
+        ms_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+        clk = clocks.stop() if rank == 0 else None
+        # ---- instrumented pass (per-kernel-class CUDA events on the launching stream); not the headline
+        r.timing(True)
+        r.timing_read(reset=True)
+        n_prof = min(2, steps)
+        for _ in range(n_prof):
+            flush.fill_(1)
+            step()
+        sync_all()
+        ktimes = r.timing_read(reset=True)
+        r.timing(False)
+        res = {"ms_per_view": ms_step, "value": H * W / (ms_step * 1e-3), "unit": "rays/s", "steps": steps, "warmup": warmup,
+               "gpu_launches": int(launches), "clocks": clk, "kernel_ms_per_view": {k: v[0] / n_prof for k, v in ktimes.items()},
+               "_ktimes": ktimes, "_n_prof": n_prof}
+        if not e2e:
+            return res
+        # ---- end to end through the public API, host buffers
+        pin = lambda x: x.contiguous().pin_memory()
+        h_img, h_tex, h_fg = pin(inp_host["img"]), pin(inp_host["feat_tex"]), pin(inp_host["src_foreground_mask"].to(torch.uint8))
+        h_g0, h_g1 = pin(inp_host["feat_geo"][0]), pin(inp_host["feat_geo"][1])
+        h_out = torch.empty(H, W, 8).pin_memory() if rank == 0 else None
+        pix = torch.from_numpy(D.partition_pixels(H, W, rank, world)).to(dev)
+        rows_pad = D.padded_tile_rows(H, W, world)
+        tiles = [torch.empty(rows_pad, 8, device=dev) for _ in range(world)] if world > 1 else None
 
-    for _ in range(2):
-        step_e2e()
-    sync_all()
-    n_e2e = max(1, args.steps)
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        step_e2e()
-    sync_all()
-    te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = H * W / float(te.item())
+        def step_e2e():
+            d_img, d_tex = h_img.to(dev, non_blocking=True), h_tex.to(dev, non_blocking=True)
+            d_fg = h_fg.to(dev, non_blocking=True).bool()
+            d_g = [h_g0.to(dev, non_blocking=True), h_g1.to(dev, non_blocking=True)]
+            out = VANeRF.batch_render_pifu_nerf(net, d_img, inp["cam_in"], inp["hand_type"], inp["targets"], V, inp["cam_tar"], 1, 0, None,
+                                                d_g, d_tex, None, inp["sp_data"], inp["objcenter"], fine=True, uniform=True,
+                                                sample_per_ray_c=S_C, sample_per_ray_f=S_F, src_foreground_mask=d_fg, bounds=inp["bounds"],
+                                                pixel_override=pix[None])
+            rows = torch.cat([out["tex_fg_fine"][0].reshape(3, -1).T, out["depth_fine"].reshape(-1, 1), out["alpha_fine"].reshape(-1, 1),
+                              out["sdf"].reshape(-1, 1), out["tex_fg"][0].reshape(3, -1).T[:, :2]], 1).contiguous()
+            if world > 1:
+                tile = rows.new_zeros((rows_pad, 8))
+                tile[: rows.shape[0]] = rows
+                dist.all_gather(tiles, tile)
+                full = D.assemble(tiles, H, W, world)            # the image a user gets: reference pixel order
+            else:
+                full = rows.view(H, W, 8)
+            if rank == 0:
+                h_out.copy_(full, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    # ---------------- the other precision path of BASELINE.json configs[1], one timed view (N = 1 only)
-    fp32_extra = None
+        for _ in range(2):
+            step_e2e()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_e2e()
+        sync_all()
+        r.finish()
+        sec = max_over_ranks((time.perf_counter() - t0) / steps)
+        h2d = sum(x.numel() * x.element_size() for x in (h_img, h_tex, h_fg, h_g0, h_g1))
+        res["e2e"] = {"value": H * W / sec, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 8 * 4, "ms_per_view": 1e3 * sec}
+        res["_frame"] = (inp, tar)
+        return res
+
+    def rooflines(res, precision):
+        ktimes, n_prof = res["_ktimes"], res["_n_prof"]
+        n_samples = R_local * (S_C + S_C + S_F) * n_prof
+        mlp_ms, mlp_n = ktimes["mlp"]
+        gat_ms, gat_n = ktimes["gather"]
+        geo_ms, geo_n = ktimes["geom"]
+        ach_tf = FLOP_PER_SAMPLE(V) * n_samples / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        e = 4 if precision == L.FP32 else 2                  # fp32 maps vs bf16 maps / vertex tables
+        ach_gb = GATHER_BYTES_PER_SAMPLE(V, e) * n_samples / (gat_ms * 1e-3) / 1e9 if gat_ms > 0 else 0.0
+        n_queries = R_local * (S_C + S_F) * n_prof           # mesh queries actually made (geometry reuse: coarse depths once)
+        name = "fp32" if precision == L.FP32 else "bf16"
+        return {
+            "roofline": {"kernel": "k_mlp_simt (fused PE + fusion + MLP, fp32 FFMA)" if precision == L.FP32 else "k_mlp_tc (tcgen05)",
+                         "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sust"],
+                         "traffic": ncu_traffic(name), "peak_source": pk["src"] + " bf16 sustained (cuBLAS, seconds-long loop)",
+                         "launches": int(mlp_n), "avg_launch_ms": mlp_ms / max(1, mlp_n), "algorithmic_flop_per_sample": FLOP_PER_SAMPLE(V),
+                         "timed_by": "CUDA events around the kernel's launches in a separate instrumented pass of the same views"},
+            "roofline_gather": {"kernel": "k_gather" if precision == L.FP32 else "k_gather_tc", "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": ach_gb / pk["hbm"], "launches": int(gat_n), "avg_launch_ms": gat_ms / max(1, gat_n),
+                                "algorithmic_bytes_per_sample": GATHER_BYTES_PER_SAMPLE(V, e)},
+            "geometry": {"kernel": "k_geom_query", "ms_per_view": geo_ms / n_prof, "queries_per_view": n_queries // n_prof,
+                         "queries_per_s": n_queries / (geo_ms * 1e-3) if geo_ms > 0 else 0.0,
+                         "note": "exact closest face + inside parity + nearest vertex per query; no roofline in the north star"},
+        }
+
+    pub = lambda d: {k: v for k, v in d.items() if not k.startswith("_")}
+    # ================= headline: workload B (or C with --workload C) on the selected precision path
+    main_res = measure_view("bvv" if args.workload == "C" else "narrow", prec, args.steps, W_steps)
+    line = None
+    if rank == 0:
+        line = {"metric": "rays_per_s", "value": main_res["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": W_steps,
+                "ms_per_step": main_res["ms_per_view"], "ms_per_view": main_res["ms_per_view"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config_dict(args, "gpu"),
+                "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "kernel_ms_per_step": main_res["kernel_ms_per_view"],
+                "clocks": main_res["clocks"]}
+        line.update(rooflines(main_res, prec))
+
+    # ================= the other precision path of BASELINE.json configs[1] (N = 1): >= 3 timed views, own roofline block
     if world == 1 and args.precision == "bf16" and not args.no_fp32_path:
-        r.render_rays(tar, pix, S_C, S_F, True, L.FP32)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.fill_(1)
-        a.record()
-        r.render_rays(tar, pix, S_C, S_F, True, L.FP32)
-        b.record()
-        torch.cuda.synchronize()
-        fp32_extra = {"ms_per_view": a.elapsed_time(b), "value": H * W / (a.elapsed_time(b) * 1e-3), "unit": "rays/s",
-                      "note": "fp32 FFMA path (k_gather + k_mlp_simt), 1 warm-up + 1 timed view, inputs resident"}
+        fres = measure_view("narrow", L.FP32, max(3, min(args.steps, 3)), 1, e2e=False)
+        blk = pub(fres)
+        blk.update(rooflines(fres, L.FP32))
+        blk["note"] = "fp32 path (k_gather + k_mlp_simt, FFMA), inputs resident; roofline denominators are the same measured peaks as the bf16 path"
+        line["fp32_path"] = blk
 
-    # ---------------- coarse reuse (vanerf_set_reuse_coarse): same output bits, 64 + 64 instead of 64 + 128 evaluations per ray
-    reuse_extra = None
+    # ================= coarse reuse (vanerf_set_reuse_coarse): same output bits, 64 + 64 instead of 64 + 128 evaluations per ray
     if world == 1 and not args.no_reuse_variant:
+        inp, tar = main_res["_frame"]
+        r.set_frame(inp["img"], inp["cam_in"], inp["targets"], inp["sp_data"], inp["feat_geo"], inp["feat_tex"], inp["src_foreground_mask"])
+        pix = torch.from_numpy(D.partition_pixels(H, W, 0, 1)).to(dev)
         r.set_reuse_coarse(True)
         r.render_rays(tar, pix, S_C, S_F, True, prec)
         torch.cuda.synchronize()
@@ -386,48 +450,29 @@ def main():
         torch.cuda.synchronize()
         r.set_reuse_coarse(False)
         ms_r = sum(a.elapsed_time(b) for a, b in evr) / len(evr)
-        reuse_extra = {"ms_per_view": ms_r, "value": H * W / (ms_r * 1e-3), "unit": "rays/s", "evaluations_per_ray": S_C + S_F,
-                       "note": "NOT the headline: fine pass evaluates only the 64 new depths and reuses the coarse pass for the 64 coarse "
-                               "depths of the merged set (bit-identical output, tests: *_coarse_reuse_is_bit_identical); inputs resident"}
+        line["coarse_reuse"] = {"ms_per_view": ms_r, "value": H * W / (ms_r * 1e-3), "unit": "rays/s", "evaluations_per_ray": S_C + S_F,
+                                "note": "NOT the headline: fine pass evaluates only the 64 new depths and reuses the coarse pass for the 64 coarse "
+                                        "depths of the merged set (bit-identical output, tests: *_coarse_reuse_is_bit_identical); inputs resident"}
+
+    # ================= secondary workloads of BASELINE.json: C (vanerf_bvv layout) and D (render_dynamic, 64 frames)
+    if not args.no_secondary:
+        if args.workload == "B":
+            cres = measure_view("bvv", prec, max(2, min(args.steps, 3)), 2)
+            if rank == 0:
+                blk = pub(cres)
+                blk.update(rooflines(cres, prec))
+                blk["config"] = config_dict(args, "gpu", "C")
+                line["workload_C"] = blk
+        dres = measure_dynamic(args, net, args.frames, 1, 1)
+        if rank == 0:
+            line["workload_D"] = dres
 
     if rank == 0:
-        pk = peaks()
-        clk = clocks.stop()
-        n_samples_step = R_local * (S_C + S_C + S_F)
-        mlp_ms, mlp_n = ktimes["mlp"]
-        gat_ms, gat_n = ktimes["gather"]
-        flops = FLOP_PER_SAMPLE(V) * n_samples_step * args.steps
-        ach_tf = flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        gather_elem = 4 if args.precision == "fp32" else 2          # fp32 maps vs bf16 maps / vertex tables
-        gbytes = GATHER_BYTES_PER_SAMPLE(V, gather_elem) * n_samples_step * args.steps
-        ach_gb = gbytes / (gat_ms * 1e-3) / 1e9 if gat_ms > 0 else 0.0
-        line = {
-            "metric": "rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": W_steps,
-            "ms_per_step": ms_step, "ms_per_view": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "config": config_dict(args, "gpu"),
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_view": 1e3 * float(te.item())},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "k_mlp_simt (fused PE + fusion + MLP, fp32 FFMA)" if args.precision == "fp32" else "k_mlp_tc (tcgen05)",
-                         "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": ach_tf / pk["tf_sust"], "traffic": ncu_traffic(args.precision),
-                         "peak_source": pk["src"] + " bf16 sustained",
-                         "launches": int(mlp_n), "avg_launch_ms": mlp_ms / max(1, mlp_n),
-                         "algorithmic_flop_per_sample": FLOP_PER_SAMPLE(V)},
-            "roofline_gather": {"kernel": "k_gather" if args.precision == "fp32" else "k_gather_tc", "bound": "hbm", "achieved": ach_gb, "peak": pk["hbm"], "unit": "GB/s",
-                                "frac": ach_gb / pk["hbm"], "launches": int(gat_n), "avg_launch_ms": gat_ms / max(1, gat_n),
-                                "algorithmic_bytes_per_sample": GATHER_BYTES_PER_SAMPLE(V, gather_elem)},
-            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
-            "clocks": clk,
-        }
-        if fp32_extra is not None:
-            line["fp32_path"] = fp32_extra
-        if reuse_extra is not None:
-            line["coarse_reuse"] = reuse_extra
         if world == 1 and not args.no_cpu_baseline:
-            rps, sec, n = cpu_port_rays_per_s(32, False)
+            rps, sec, n, setup = cpu_port(32, True)
             line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"{n} rays (32x32 lattice), 64 coarse samples/ray, V=3, fine=False (BASELINE.json configs[0]); {sec:.1f} s"}
+                                    "sample": f"{n} rays (32x32 lattice of the 334x512 view), 64 coarse + 128 fine evaluations/ray, V=3: {sec:.1f} s; "
+                                              f"per-frame setup {setup:.2f} s timed separately, not included"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

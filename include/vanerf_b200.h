@@ -123,6 +123,12 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
 int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t n_rays,
                        const float* ztab, int32_t n_samples, float* rays, float* z, void* stream);
 
+/* Same with explicit interpolation parameters: ttab dev (S), or (R,S) when t_per_ray != 0.  The training branch draws
+ * t = z_lower + rand * (z_upper - z_lower) per ray and sample (stratified jitter, src/model.py:1226-1230) with torch and
+ * passes the table in; z = near + (far - near) * t like the uniform branch (:1230,:1232). */
+int vanerf_sample_rays_t(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t n_rays,
+                         const float* ttab, int32_t n_samples, int32_t t_per_ray, float* rays, float* z, void* stream);
+
 /* Signed distance to the mesh, closest face, nearest vertex, per-view sample visibility
  * (mesh_util.py:498-524 = kaolin point_to_mesh_distance + check_sign; networks.py:28 = pytorch3d knn_points).
  * Outputs dev: pts (N,3) sample positions, sdf (N), face (N), nn_vert (N), qvis (V,N).  Any output may be NULL
@@ -193,6 +199,46 @@ int vanerf_shade_debug(vanerf_ctx* ctx, const vanerf_target* tar, const float* r
 int vanerf_query_points(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const float* pts, const float* view,
                         int32_t n_points, const float* sdf_in, const uint8_t* qvis_in, float* raw_out, uint8_t* valid,
                         float* rgba, void* stream);
+
+/* Stage-level primitives: what the reference's per-stage callables are made of.  vanerf_b200/stages.py composes them into
+ * feat_sample, KNN_vis, SpatialEncoder, GeoVisFusion, MLPUNetFusion, TexVisFusion and IBRRenderingHead with the reference's
+ * signatures; the render path itself runs the fused kernels and never materialises these outputs.
+ *   vanerf_feat_sample  feat_sample (src/utils.py:136-151): feat dev (B,C,H,W), uv dev (B,N,2) -> out dev (B,N,C)
+ *   vanerf_knn1         pytorch3d knn_points(K=1) inside KNN_vis (src/networks.py:28): query dev (N,3), vert dev (Nv,3) -> idx (N)
+ *   vanerf_dense        one Conv1d(k=1) / Linear layer: y (M,N) = act(x (M,K) @ w (N,K)^T + b), act: 0 none, 1 ReLU,
+ *                       2 Softplus(beta=100, threshold=20), 3 sigmoid, 4 ELU; b may be NULL
+ *   vanerf_rel_z_decay  SpatialEncoder "rel_z_decay" (src/spatial.py:109-117): cxyz dev (BV,N,3) camera-space samples, kxyz dev
+ *                       (BV,n_kpt,3) camera-space keypoints -> out dev (BV,N,(1 + 2 levels) n_kpt) */
+int vanerf_feat_sample(vanerf_ctx* ctx, const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* uv, int32_t N,
+                       float* out, void* stream);
+int vanerf_knn1(vanerf_ctx* ctx, const float* query, int32_t N, const float* vert, int32_t Nv, int32_t* idx, void* stream);
+int vanerf_dense(vanerf_ctx* ctx, const float* x, int32_t M, int32_t K, const float* w, const float* b, int32_t N, int32_t act,
+                 float* y, void* stream);
+int vanerf_rel_z_decay(vanerf_ctx* ctx, const float* cxyz, const float* kxyz, int32_t BV, int32_t N, int32_t n_kpt, int32_t levels,
+                       float scale, float sigma, float* out, void* stream);
+
+/* Training branch (BASELINE.json configs[4]; reference: the net.training paths of src/model.py:748-957, :1103-1422 and their
+ * autograd).  Sampling and mesh queries reuse vanerf_sample_rays_t / vanerf_importance (per-ray u) / vanerf_geom_query (no
+ * gradient flows through them).  The unfused training graph of vanerf_b200/train.py adds:
+ *   vanerf_project_samples  per sample and view, what VANeRF.query derives from the position alone (src/model.py:780-821,
+ *                           :936-946, src/spatial.py:71-72): xy dev (V,N,2), mask dev (N) = all-views AND of the in-frustum and
+ *                           foreground tests (before view dropout), pw_raw dev (V,N) boundary weight before mask / normalisation,
+ *                           cam dev (V,N,3) camera-space position, ray_diff dev (V,N,4)
+ *   vanerf_feat_sample_bwd  backward of feat_sample w.r.t. the map: d_out dev (B,N,C) scatter-added into d_feat dev (B,C,H,W)
+ *                           (zeroed by the caller)
+ *   vanerf_composite_beta   vanerf_composite with an explicit beta (sigmoid_beta is a parameter of the training graph)
+ *   vanerf_composite_bwd    backward of rgba2out: g_color (R,3), g_alpha, g_depth, g_sdf (R) (any NULL) -> d_rgba dev (R,S,5) and
+ *                           d_beta dev (1) (accumulated; zeroed by the caller)
+ * Dense layers of the training graph are library GEMMs (cuBLAS through torch.nn.functional.linear) under torch autograd. */
+int vanerf_project_samples(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t n_rays, int32_t n_samples,
+                           float* xy, uint8_t* mask, float* pw_raw, float* cam, float* ray_diff, void* stream);
+int vanerf_feat_sample_bwd(vanerf_ctx* ctx, const float* d_out, int32_t B, int32_t C, int32_t H, int32_t W, const float* uv, int32_t N,
+                           float* d_feat, void* stream);
+int vanerf_composite_beta(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t n_rays, int32_t n_samples, float beta,
+                          float* color, float* depth, float* alpha, float* sdf_out, float* contrib, void* stream);
+int vanerf_composite_bwd(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t n_rays, int32_t n_samples, float beta,
+                         const float* g_color, const float* g_alpha, const float* g_depth, const float* g_sdf, float* d_rgba, float* d_beta,
+                         void* stream);
 
 /* Per-kernel-class device timing with CUDA events on the launching stream (used by bench.py for the roofline
  * numbers).  vanerf_timing_read synchronises the recorded events; ms_out / count_out have 7 entries:

@@ -15,30 +15,37 @@ from vanerf_b200 import _lib as L
 from vanerf_b200 import synthetic, weights
 from vanerf_b200.renderer import Renderer
 
+# ---- the bars -------------------------------------------------------------------------------------------------------
+# (1) BASELINE.json north_star, asserted literally on PER-PIXEL outputs (composited rgb, alpha, depth; coarse pass, and fine
+#     pass evaluated on the oracle's fine depths): 1e-3 max-abs for the fp32 path, 1e-2 for the bf16-MLP path.  No scaling
+#     by the output range.
 TOL_FP32 = 1e-3
 TOL_BF16 = 1e-2
-
-
-def tol_for(precision, ref):
-    """fp32 path: 1e-3 max-abs.  bf16-MLP path: 1e-2 max-abs on outputs in the unit range (every reference-init case and
-    all colours a real model produces); the synthetic stress weights drive per-sample outputs up to |2.5|, where the
-    bar is 1e-2 of the output range."""
-    if precision == L.FP32:
-        return TOL_FP32
-    return TOL_BF16 * max(1.0, float(np.abs(np.asarray(ref)).max()))
-
-
+# (2) PER-SAMPLE taps (pooled latent, VANeRF.query output, rgba before compositing) are not what the north star bounds.
+#     fp32 path: 1e-3 as everywhere.  bf16 path: a dozen bf16-rounded layers in a row leave ~1 % of the output range on the
+#     O(1) synthetic 'stress' weights (|out| up to 2.5; 1e-4 on reference-init weights), so these are held to 2e-2 of the
+#     range; compositing averages that noise down to the per-pixel bar (1).
 TOL_BF16_SAMPLE = 2e-2
+# (3) END-TO-END fine pass (vanerf_render_rays: the kernel path's OWN fine depths).  importance_sample inverts a cdf, which
+#     amplifies last-ulp differences of `contrib` into depth shifts: the reference and its own CPU restatement already differ
+#     by 1.2e-3 in fine colour on the stress weights (tests/test_oracle_golden.py).  fp32 path: 5e-3; bf16 path: 2e-2.  The
+#     1e-3 / 1e-2 bars of (1) hold "given identical fine depths" and are asserted that way in check_all.
+TOL_E2E_FINE_FP32 = 5e-3
+TOL_E2E_FINE_BF16 = 2e-2
+
+
+def tol_pixel(precision):
+    return TOL_FP32 if precision == L.FP32 else TOL_BF16
 
 
 def tol_sample(precision, ref):
-    """Per-SAMPLE network outputs (latent, query out, rgba before compositing).  BASELINE.json's bf16 bar (1e-2) is on
-    per-pixel RGB / alpha, which `tol_for` enforces on the composited outputs.  Per sample, a dozen bf16-rounded
-    layers in a row leave ~1% of the output range on the O(1) synthetic stress weights (1e-4 on reference-init
-    weights), so the intermediate quantities are held to 2e-2 of the range; fp32 path: 1e-3 as everywhere."""
     if precision == L.FP32:
         return TOL_FP32
     return TOL_BF16_SAMPLE * max(1.0, float(np.abs(np.asarray(ref)).max()))
+
+
+def tol_e2e_fine(precision):
+    return TOL_E2E_FINE_FP32 if precision == L.FP32 else TOL_E2E_FINE_BF16
 
 
 def lattice_pixels(H, W, npix):
@@ -91,7 +98,7 @@ def assert_close(name, got, ref, tol):
 
 def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, S_f=64, report=None):
     """Runs every stage on `r` and compares with the oracle.  Returns a dict of max-abs errors."""
-    tol = TOL_FP32 if precision == L.FP32 else TOL_BF16
+    tol = tol_pixel(precision)
     orc = OT.Oracle(sd, inp)
     ot = {}
     oo = orc.render(fine=True, pixels=pixels, S_c=S_c, S_f=S_f, taps=ot)
@@ -136,7 +143,7 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
                                    assert_close("composite alpha", _np(comp_o["alpha"]), ref_c["alpha"], 1e-5),
                                    assert_close("composite sdf", _np(comp_o["sdf"]), ref_c["sdf"], 1e-5))
     comp = r.composite(rgba, z, geo["sdf"].view(z.shape))
-    errs["tex_fg"] = assert_close("tex_fg", _np(comp["color"]), oo["tex_fg"], tol_for(precision, oo["tex_fg"]))
+    errs["tex_fg"] = assert_close("tex_fg", _np(comp["color"]), oo["tex_fg"], tol)
     errs["depth"] = assert_close("depth", _np(comp["depth"]), oo["depth"], tol)
     errs["alpha"] = assert_close("alpha", _np(comp["alpha"]), oo["alpha"], tol)
     # ---- importance sampling + merge given the oracle's contrib: bit-exact fine depths
@@ -153,22 +160,23 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
     assert_exact("fine valid", _np(valid2) > 0, ot["valid_fine"])
     errs["rgba_fine"] = assert_close("rgba fine", _np(rgba2), ot["rgba_fine"], tol_sample(precision, ot["rgba_fine"]))
     comp2 = r.composite(rgba2, z2, geo2["sdf"].view(z2.shape))
-    errs["tex_fg_fine"] = assert_close("tex_fg_fine", _np(comp2["color"]), oo["tex_fg_fine"], tol_for(precision, oo["tex_fg_fine"]))
+    errs["tex_fg_fine"] = assert_close("tex_fg_fine (oracle's fine depths)", _np(comp2["color"]), oo["tex_fg_fine"], tol)
+    errs["alpha_fine"] = assert_close("alpha fine", _np(comp2["alpha"]), oo["alpha_fine"], tol)
+    errs["depth_fine"] = assert_close("depth fine", _np(comp2["depth"]), oo["depth_fine"], tol)
     errs["sdf_fine"] = assert_close("sdf fine", _np(comp2["sdf"]), oo["sdf"], tol)
     return errs, oo, ot
 
 
 def check_render_rays(r: Renderer, inp, oo, pixels, precision=L.FP32, tol_fine=None):
-    """The fused entry point (coarse + importance + fine in one call) against the oracle's end-to-end render."""
-    tol = TOL_FP32 if precision == L.FP32 else TOL_BF16
+    """The fused entry point (coarse + importance + fine in one call) against the oracle's end-to-end render: coarse pass at
+    the per-pixel bar (1), fine pass (own fine depths) at the end-to-end bar (3)."""
+    tol = tol_pixel(precision)
     tar = r.make_target(inp["cam_tar"], inp["bounds"])
     oc, of = r.render_rays(tar, torch.from_numpy(pixels), 64, 64, True, precision)
     oc, of = _np(oc), _np(of)
-    e = {"rr_tex_fg": assert_close("render_rays tex_fg", oc[:, :3], oo["tex_fg"], tol_for(precision, oo["tex_fg"])),
+    e = {"rr_tex_fg": assert_close("render_rays tex_fg", oc[:, :3], oo["tex_fg"], tol),
          "rr_depth": assert_close("render_rays depth", oc[:, 3], oo["depth"], tol),
          "rr_alpha": assert_close("render_rays alpha", oc[:, 4], oo["alpha"], tol)}
-    # the fine pass re-samples from a cdf: its depths amplify fp rounding of contrib (reference vs its own CPU
-    # restatement already differ by ~1e-3 on stress weights), hence the separate tolerance
-    e["rr_tex_fg_fine"] = assert_close("render_rays tex_fg_fine", of[:, :3], oo["tex_fg_fine"],
-                                       (tol_fine or tol) * (1.0 if precision == L.FP32 else max(1.0, float(np.abs(oo["tex_fg_fine"]).max()))))
+    e["rr_tex_fg_fine"] = assert_close("render_rays tex_fg_fine (own fine depths)", of[:, :3], oo["tex_fg_fine"], tol_fine or tol_e2e_fine(precision))
+    e["rr_alpha_fine"] = assert_close("render_rays alpha_fine", of[:, 4], oo["alpha_fine"], tol)
     return e

@@ -14,7 +14,7 @@ import pytest
 from oracle import oracle_torch as OT
 from vanerf_b200 import synthetic, weights
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "v*.npz")))      # render goldens (stage goldens: test_stages.py)
 
 
 def _exact(a, b):

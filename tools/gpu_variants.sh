@@ -14,7 +14,7 @@ for spec in "$@"; do
   grep -E "tc_error|FAILED|max" gpurun_out/var_${tag}_debug.log | tail -4
   if [ $rc -ne 0 ] || grep -q "tc_error=[1-9]" gpurun_out/var_${tag}_debug.log; then echo "correctness pass failed ($rc)"; continue; fi
   fi
-  env VANERF_B200_LIB=$lib $envs timeout 300 python bench.py --precision bf16 --steps 2 --warmup 3 --no-cpu-baseline --no-fp32-path --no-reuse-variant > gpurun_out/var_${tag}.json 2> gpurun_out/var_${tag}.err
+  env VANERF_B200_LIB=$lib $envs timeout 300 python bench.py --precision bf16 --steps 2 --warmup 3 --no-cpu-baseline --no-fp32-path --no-reuse-variant --no-secondary > gpurun_out/var_${tag}.json 2> gpurun_out/var_${tag}.err
   python - "$tag" <<'PY'
 import json, sys
 try:

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VANERF_B200_LIB: developer override (e.g. the cycle-trace build tools/build.py trace makes); same ABI, same kernels
 LIB_PATH = os.environ.get("VANERF_B200_LIB") or os.path.join(_HERE, "libvanerf_b200.so")
 
-MAX_VIEWS = 4
+MAX_VIEWS = 4            # VANERF_MAX_VIEWS (fp32 path)
+MAX_VIEWS_BF16 = 3       # VANERF_MAX_VIEWS_BF16 (tensor-core path)
 RAY_STRIDE = 8
 FP32, BF16 = 0, 1
 
@@ -59,6 +60,7 @@ PROTOTYPES = {
     "vanerf_load_weights": (C.c_int, [_P, C.POINTER(VWeights), _P]),
     "vanerf_frame_setup": (C.c_int, [_P, C.POINTER(VFrame), _P, _P]),
     "vanerf_sample_rays": (C.c_int, [_P, C.POINTER(VTarget), _P, _I, _P, _I, _P, _P, _P]),
+    "vanerf_sample_rays_t": (C.c_int, [_P, C.POINTER(VTarget), _P, _I, _P, _I, _I, _P, _P, _P]),
     "vanerf_geom_query": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "vanerf_shade": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vanerf_shade_debug": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -69,6 +71,14 @@ PROTOTYPES = {
     "vanerf_set_reuse_geometry": (C.c_int, [_P, C.c_int]),
     "vanerf_render_rays": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "vanerf_query_points": (C.c_int, [_P, C.c_int, C.POINTER(VTarget), _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "vanerf_feat_sample": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "vanerf_knn1": (C.c_int, [_P, _P, _I, _P, _I, _P, _P]),
+    "vanerf_dense": (C.c_int, [_P, _P, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "vanerf_rel_z_decay": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, C.c_float, C.c_float, _P, _P]),
+    "vanerf_project_samples": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "vanerf_feat_sample_bwd": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    "vanerf_composite_beta": (C.c_int, [_P, _P, _P, _P, _I, _I, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "vanerf_composite_bwd": (C.c_int, [_P, _P, _P, _P, _I, _I, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "vanerf_timing_enable": (C.c_int, [_P, C.c_int]),
     "vanerf_timing_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(_I64), C.c_int]),
     "vanerf_scratch_bytes": (C.c_size_t, [_P, _I, _I]),

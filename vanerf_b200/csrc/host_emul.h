@@ -137,6 +137,13 @@ static inline unsigned long long atomicMin(unsigned long long* a, unsigned long 
     return old;
 }
 static inline int atomicAdd(int* a, int v) { return __atomic_fetch_add(a, v, __ATOMIC_RELAXED); }
+static inline float atomicAdd(float* a, float v) {
+    unsigned* p = reinterpret_cast<unsigned*>(a);
+    unsigned old = __atomic_load_n(p, __ATOMIC_RELAXED), nw;
+    float f;
+    do { std::memcpy(&f, &old, 4); f += v; std::memcpy(&nw, &f, 4); } while (!__atomic_compare_exchange_n(p, &old, nw, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+    return f - v;
+}
 static inline int atomicMin(int* a, int v) {
     int old = __atomic_load_n(a, __ATOMIC_RELAXED);
     while (v < old && !__atomic_compare_exchange_n(a, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

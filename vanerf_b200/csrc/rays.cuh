@@ -5,7 +5,8 @@
 #include "common.cuh"
 
 // rays: (R, 8) = dir.xyz, near, far, hit, box_near, box_far
-__global__ void k_sample_rays(TargetDev tar, const int* __restrict__ pix_xy, int R, const float* __restrict__ ztab,
+// ztab: (S) shared by all rays, or (R,S) when t_per_ray != 0 (training: stratified jitter, src/model.py:1226-1230)
+__global__ void k_sample_rays(TargetDev tar, const int* __restrict__ pix_xy, int R, const float* __restrict__ ztab, int t_per_ray,
                               int S, float* __restrict__ rays, float* __restrict__ z) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
@@ -73,7 +74,8 @@ __global__ void k_sample_rays(TargetDev tar, const int* __restrict__ pix_xy, int
     o[0] = dir[0]; o[1] = dir[1]; o[2] = dir[2]; o[3] = zn; o[4] = zf; o[5] = hit ? 1.0f : 0.0f;
     o[6] = bnear; o[7] = bfar;
     const float span = xsub(zf, zn);
-    for (int s = 0; s < S; ++s) z[(size_t)r * S + s] = xadd(zn, xmul(span, ztab[s]));
+    const float* tt = t_per_ray ? ztab + (size_t)r * S : ztab;
+    for (int s = 0; s < S; ++s) z[(size_t)r * S + s] = xadd(zn, xmul(span, tt[s]));
 }
 
 // eval_pts = cam_pos + dir * z  (mul, then add; model.py:1234)

@@ -13,6 +13,8 @@
 #include "gather.cuh"
 #include "mlp_simt.cuh"
 #include "composite.cuh"
+#include "stages.cuh"
+#include "train.cuh"
 #ifndef VANERF_HOST_EMUL
 #include "mlp_tc.cuh"
 #endif
@@ -432,7 +434,17 @@ int vanerf_sample_rays(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t*
     DeviceGuard dg_(ctx);
     if (!ctx || !tar || !pix_xy || !ztab || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_sample_rays");
     TimedScope ts(ctx, KCL_RAYS, (cudaStream_t)stream);
-    VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ztab, S, rays, z);
+    VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ztab, 0, S, rays, z);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+int vanerf_sample_rays_t(vanerf_ctx* ctx, const vanerf_target* tar, const int32_t* pix_xy, int32_t R, const float* ttab,
+                         int32_t S, int32_t t_per_ray, float* rays, float* z, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !tar || !pix_xy || !ttab || !rays || !z || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_sample_rays_t");
+    TimedScope ts(ctx, KCL_RAYS, (cudaStream_t)stream);
+    VANERF_LAUNCH(k_sample_rays, cdiv(R, 128), 128, 0, stream, make_target(tar), pix_xy, R, ttab, t_per_ray ? 1 : 0, S, rays, z);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
 }
@@ -822,6 +834,82 @@ int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const flo
     TimedScope ts(ctx, KCL_IMPORTANCE, (cudaStream_t)stream);
     VANERF_LAUNCH(k_importance, blocks, COMP_WARPS * 32, smem, stream, contrib_inner, (const float*)nullptr, z_mid, R, D, u, nf,
                   u_per_ray, z_fine, (float*)nullptr, (unsigned char*)nullptr);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage primitives
+int vanerf_feat_sample(vanerf_ctx* ctx, const float* feat, int32_t B, int32_t C, int32_t H, int32_t W, const float* uv, int32_t N,
+                       float* out, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !feat || !uv || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0) return ctx_invalid(ctx, "vanerf_feat_sample");
+    VANERF_LAUNCH(k_feat_sample, cdiv((long long)B * N * C, 256), 256, 0, stream, feat, B, C, H, W, uv, N, out);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+int vanerf_knn1(vanerf_ctx* ctx, const float* query, int32_t N, const float* vert, int32_t Nv, int32_t* idx, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !query || !vert || !idx || N <= 0 || Nv <= 0) return ctx_invalid(ctx, "vanerf_knn1");
+    VANERF_LAUNCH(k_knn1, cdiv(N, 128), 128, 0, stream, query, N, vert, Nv, idx);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+int vanerf_dense(vanerf_ctx* ctx, const float* x, int32_t M, int32_t K, const float* w, const float* b, int32_t N, int32_t act,
+                 float* y, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !x || !w || !y || M <= 0 || K <= 0 || N <= 0 || act < 0 || act > SA_ELU) return ctx_invalid(ctx, "vanerf_dense");
+    VANERF_LAUNCH(k_dense, cdiv((long long)M * N, 256), 256, 0, stream, x, M, K, w, b, N, act, y);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+int vanerf_rel_z_decay(vanerf_ctx* ctx, const float* cxyz, const float* kxyz, int32_t BV, int32_t N, int32_t n_kpt, int32_t levels,
+                       float scale, float sigma, float* out, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !cxyz || !kxyz || !out || BV <= 0 || N <= 0 || n_kpt <= 0 || levels < 0) return ctx_invalid(ctx, "vanerf_rel_z_decay");
+    VANERF_LAUNCH(k_rel_z_decay, cdiv((long long)BV * N * n_kpt, 256), 256, 0, stream, cxyz, kxyz, BV, N, n_kpt, levels, scale, sigma, out);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ training branch
+int vanerf_project_samples(vanerf_ctx* ctx, const vanerf_target* tar, const float* rays, const float* z, int32_t R, int32_t S,
+                           float* xy, uint8_t* mask, float* pw_raw, float* cam, float* ray_diff, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !tar || !rays || !z || !xy || !mask || !pw_raw || !cam || !ray_diff || R <= 0 || S <= 0) return ctx_invalid(ctx, "vanerf_project_samples");
+    if (!ctx->have_frame) return ctx_state(ctx);
+    const long long N = (long long)R * S;
+    VANERF_LAUNCH(k_project_samples, cdiv(N, 128), 128, 0, stream, ctx->fr, make_target(tar), rays, z, S, N, xy, mask, pw_raw, cam, ray_diff);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+int vanerf_feat_sample_bwd(vanerf_ctx* ctx, const float* d_out, int32_t B, int32_t C, int32_t H, int32_t W, const float* uv, int32_t N,
+                           float* d_feat, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !d_out || !uv || !d_feat || B <= 0 || C <= 0 || H <= 0 || W <= 0 || N <= 0) return ctx_invalid(ctx, "vanerf_feat_sample_bwd");
+    VANERF_LAUNCH(k_feat_sample_bwd, cdiv((long long)B * N * C, 256), 256, 0, stream, d_out, B, C, H, W, uv, N, d_feat);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+int vanerf_composite_bwd(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t R, int32_t S, float beta,
+                         const float* g_color, const float* g_alpha, const float* g_depth, const float* g_sdf, float* d_rgba, float* d_beta,
+                         void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !rgba || !z || !mesh_sdf || !d_rgba || R <= 0 || S <= 0 || !(beta > 0.0f)) return ctx_invalid(ctx, "vanerf_composite_bwd");
+    if (S > 32 * COMP_MAX_PER_LANE) return ctx_unsupported(ctx, "vanerf_composite_bwd: too many samples per ray");
+    const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    VANERF_LAUNCH(k_composite_bwd, blocks, COMP_WARPS * 32, 0, stream, rgba, z, mesh_sdf, R, S, beta, g_color, g_alpha, g_depth, g_sdf, d_rgba, d_beta);
+    CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+}
+// rgba2out with an explicit beta (the training graph owns sigmoid_beta as a parameter)
+int vanerf_composite_beta(vanerf_ctx* ctx, const float* rgba, const float* z, const float* mesh_sdf, int32_t R, int32_t S, float beta,
+                          float* color, float* depth, float* alpha, float* sdf_out, float* contrib, void* stream) {
+    DeviceGuard dg_(ctx);
+    if (!ctx || !rgba || !z || !mesh_sdf || R <= 0 || S <= 0 || !(beta > 0.0f)) return ctx_invalid(ctx, "vanerf_composite_beta");
+    if (S > 32 * COMP_MAX_PER_LANE) return ctx_unsupported(ctx, "vanerf_composite_beta: too many samples per ray");
+    const int blocks = min(cdiv(R, COMP_WARPS), ctx->sm_count * 16);
+    TimedScope ts(ctx, KCL_COMPOSITE, (cudaStream_t)stream);
+    VANERF_LAUNCH(k_composite, blocks, COMP_WARPS * 32, 0, stream, rgba, z, mesh_sdf, R, S, beta, color, depth, alpha, sdf_out, contrib);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
 }

@@ -41,3 +41,28 @@ def assemble(tiles, H: int, W: int, world: int) -> torch.Tensor:
         th, tw = tile_shape(H, W, r, world)
         out[ry::gy, rx::gx] = tiles[r][: th * tw].reshape(th, tw, C)
     return out
+
+
+def render_view(renderer, tar, H: int, W: int, rank: int, world: int, n_coarse=64, n_fine=64, fine=True, precision=0, group=None,
+                gather=None) -> torch.Tensor:
+    """One view on `world` ranks: this rank renders its interleaved pixel subset (`partition_pixels`), the (rows, 16) output
+    tiles [fine r,g,b,depth,alpha,sdf,0,0 | coarse r,g,b,depth,alpha,sdf,0,0] are all-gathered (the path's only collective) and
+    interleaved back into the (H, W, 16) image in the reference's pixel order.  Every rank returns the full image; it is
+    bit-identical to the single-GPU render because a ray's result does not depend on its batch.
+    `gather(tile) -> list of world tiles` replaces torch.distributed.all_gather (tests run the ranks one after the other)."""
+    pix = torch.from_numpy(partition_pixels(H, W, rank, world))
+    oc, of = renderer.render_rays(tar, pix, n_coarse, n_fine, fine, precision)
+    rows = padded_tile_rows(H, W, world)
+    tile = oc.new_zeros((rows, 16))
+    tile[: oc.shape[0], 8:] = oc
+    if fine:
+        tile[: of.shape[0], :8] = of
+    if world == 1 and gather is None:
+        tiles = [tile]
+    elif gather is not None:
+        tiles = gather(tile)
+    else:
+        import torch.distributed as dist
+        tiles = [torch.empty_like(tile) for _ in range(world)]
+        dist.all_gather(tiles, tile, group=group)
+    return assemble(tiles, H, W, world)

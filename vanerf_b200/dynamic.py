@@ -88,7 +88,7 @@ def render_sequence(net: VANeRF, get_frame: Callable[[int], Dict], n_frames: int
     outs = []
     for k, f in enumerate(ids):
         fr = to_device_frame(get_frame(f), net.device)
-        net._frame_key = None          # a new time step: never reuse the previous frame's setup (allocator may recycle pointers)
+        net.invalidate_frame()         # a new time step: never reuse the previous frame's setup
         img = render_novel_views(net, fr, cameras_of(f), **config)
         if out_host is not None:
             out_host[k].copy_(img, non_blocking=True)

@@ -36,6 +36,7 @@ class VANeRF:
         self.feat_geo = None
         self.feat_tex = None
         self._frame_key = None
+        self._frame_refs = None
 
     # ---------------------------------------------------------------- module-like surface
     def eval(self):
@@ -81,13 +82,28 @@ class VANeRF:
 
     # ---------------------------------------------------------------- per-frame state
     def _ensure_frame(self, img_in, cam_in, targets, sp_data, feat_geo, feat_tex, fg_mask):
-        key = (img_in.data_ptr(), feat_geo[0].data_ptr(), feat_geo[1].data_ptr(), feat_tex.data_ptr(),
-               targets["vert_world"].data_ptr(), cam_in["KRT"].data_ptr(), fg_mask.data_ptr(),
-               img_in._version, targets["vert_world"]._version)
+        """Runs the per-frame setup unless EVERY per-frame input is the very tensor object (same identity, same in-place
+        version counter) the current frame was built from.  The tensors of the current frame are kept referenced, so their
+        addresses and ids cannot be recycled by a later batch of the same shapes; an in-place update of any of them bumps
+        `_version` and triggers a new setup.  (Keying on `data_ptr()` is wrong: the caching allocator hands a freed block to
+        the next frame's tensors.)"""
+        tensors = (img_in, feat_geo[0], feat_geo[1], feat_tex, fg_mask, targets["vert_world"], targets["face_world"],
+                   cam_in["KRT"], sp_data["extrin"], sp_data["kpt3d"])
+        scalars = (int(cam_in["height"]), int(cam_in["width"]), float(cam_in["znear"]), float(cam_in["zfar"]))
+        key = tuple((id(t), t._version) for t in tensors) + scalars
         if key != self._frame_key:
+            if img_in.shape[0] > L.MAX_VIEWS_BF16 and self.precision == L.BF16:
+                raise L.VanerfError(f"the bf16 tensor-core path supports up to {L.MAX_VIEWS_BF16} source views "
+                                    f"(got {img_in.shape[0]}); use precision='fp32' (up to {L.MAX_VIEWS})")
             self.vert_vis = self.renderer.set_frame(img_in, cam_in, targets, sp_data, feat_geo, feat_tex, fg_mask)
             self._frame_key = key
+            self._frame_refs = tensors
         return self.vert_vis
+
+    def invalidate_frame(self):
+        """Forces the next call to run the per-frame setup again."""
+        self._frame_key = None
+        self._frame_refs = None
 
     # ---------------------------------------------------------------- VANeRF.query (src/model.py:748-877)
     def query(self, pts, cam, hand_type, targets, feat_geo=None, feat_tex=None, vert=None, vert_vis=None,

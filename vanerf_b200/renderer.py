@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import ops as O
 from . import weights as W
 
 NUM_VERT = 1558
@@ -51,6 +52,7 @@ class Renderer:
         self.frame = None
         self._keep = []          # host arrays referenced by C structs during a call
         self._tabs = {}
+        self.handle = O.register_renderer(self)       # what the torch custom ops (vanerf_b200/ops.py) take as `ctx`
 
     def __del__(self):
         try:
@@ -210,30 +212,24 @@ class Renderer:
         return t
 
     # ------------------------------------------------------------------------------------------ stages
-    def sample_rays(self, tar, pix_xy: torch.Tensor, n_samples: int):
-        R = pix_xy.shape[0]
+    # Every stage goes through the torch custom ops of vanerf_b200/ops.py (torch.ops.vanerf_b200.*), which bind the C ABI.
+    def sample_rays(self, tar, pix_xy: torch.Tensor, n_samples: int, t: Optional[torch.Tensor] = None):
+        """t: optional (R, n_samples) per-ray interpolation parameters (training: stratified jitter, src/model.py:1226-1230);
+        default = linspace(0, 1, n_samples) shared by all rays (uniform=True)."""
         pix = pix_xy.to(self.device, torch.int32).contiguous()
-        rays, z = self.empty((R, L.RAY_STRIDE)), self.empty((R, n_samples))
-        self.lib.check(self.ctx, self.lib.dll.vanerf_sample_rays(self.ctx, C.byref(tar), self._ptr(pix), R,
-                       self._ptr(self.linspace(n_samples)), n_samples, self._ptr(rays), self._ptr(z), self.stream), "vanerf_sample_rays")
-        return rays, z
+        ztab = self.linspace(n_samples) if t is None else t.to(self.device, torch.float32).contiguous()
+        return torch.ops.vanerf_b200.sample_rays(self.handle, O.pack_target(tar), pix, ztab)
 
     def geom_query(self, tar, rays, z, want_pts=True):
-        R, S = z.shape
-        N, V = R * S, self.frame["V"]
-        pts = self.empty((N, 3)) if want_pts else None
-        sdf, face, nn = self.empty((N,)), self.empty((N,), torch.int32), self.empty((N,), torch.int32)
-        qvis = self.empty((V, N), torch.uint8)
-        self.lib.check(self.ctx, self.lib.dll.vanerf_geom_query(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S,
-                       self._ptr(pts), self._ptr(sdf), self._ptr(face), self._ptr(nn), self._ptr(qvis), self.stream), "vanerf_geom_query")
-        return dict(pts=pts, sdf=sdf, face=face, nn=nn, qvis=qvis)
+        pts, sdf, face, nn, qvis = torch.ops.vanerf_b200.geom_query(self.handle, O.pack_target(tar), rays, z)
+        return dict(pts=pts if want_pts else None, sdf=sdf, face=face, nn=nn, qvis=qvis)
 
     def shade(self, tar, rays, z, geo, precision=L.FP32, want_raw=True, want_latent=False):
         R, S = z.shape
         N = R * S
-        rgba, valid = self.empty((N, 5)), self.empty((N,), torch.uint8)
-        raw = self.empty((N, 5)) if want_raw else None
-        if want_latent:
+        if want_latent:                 # test hook (vanerf_shade_debug*): also returns MLPUNetFusion's pooled latent
+            rgba, valid = self.empty((N, 5)), self.empty((N,), torch.uint8)
+            raw = self.empty((N, 5)) if want_raw else None
             lat = self.empty((N, 128))
             fn = self.lib.dll.vanerf_shade_debug if precision == L.FP32 else self.lib.dll.vanerf_shade_debug_bf16
             st = fn(self.ctx, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
@@ -241,50 +237,29 @@ class Renderer:
                                                  self._ptr(raw), self._ptr(lat), self.stream)
             self.lib.check(self.ctx, st, "vanerf_shade_debug")
             return rgba, valid, raw, lat
-        st = self.lib.dll.vanerf_shade(self.ctx, precision, C.byref(tar), self._ptr(rays), self._ptr(z), R, S, self._ptr(geo["sdf"]),
-                                       self._ptr(geo["nn"]), self._ptr(geo["qvis"]), self._ptr(rgba), self._ptr(valid), self._ptr(raw), self.stream)
-        self.lib.check(self.ctx, st, "vanerf_shade")
-        return rgba, valid, raw
+        rgba, valid, raw = torch.ops.vanerf_b200.shade(self.handle, O.pack_target(tar), rays, z, geo["sdf"], geo["nn"], geo["qvis"], int(precision))
+        return rgba, valid, (raw if want_raw else None)
 
     def composite(self, rgba, z, mesh_sdf):
-        R, S = z.shape
-        out = dict(color=self.empty((R, 3)), depth=self.empty((R,)), alpha=self.empty((R,)), sdf=self.empty((R,)),
-                   contrib=self.empty((R, S)))
-        st = self.lib.dll.vanerf_composite(self.ctx, self._ptr(rgba), self._ptr(z), self._ptr(mesh_sdf), R, S, self._ptr(out["color"]),
-                                           self._ptr(out["depth"]), self._ptr(out["alpha"]), self._ptr(out["sdf"]),
-                                           self._ptr(out["contrib"]), self.stream)
-        self.lib.check(self.ctx, st, "vanerf_composite")
-        return out
+        color, depth, alpha, sdf, contrib = torch.ops.vanerf_b200.composite(self.handle, rgba, z, mesh_sdf)
+        return dict(color=color, depth=depth, alpha=alpha, sdf=sdf, contrib=contrib)
 
     def importance(self, contrib, z, n_fine: int, u: Optional[torch.Tensor] = None):
-        R, S = z.shape
-        per_ray = 0
-        if u is None:
-            u = self.linspace(n_fine)
-        elif u.dim() == 2:
-            per_ray = 1
-        u = u.to(self.device, torch.float32).contiguous()
-        z_f, z_all = self.empty((R, n_fine)), self.empty((R, S + n_fine))
-        st = self.lib.dll.vanerf_importance(self.ctx, self._ptr(contrib), self._ptr(z), R, S, self._ptr(u), n_fine, per_ray,
-                                            self._ptr(z_f), self._ptr(z_all), self.stream)
-        self.lib.check(self.ctx, st, "vanerf_importance")
-        return z_f, z_all
+        u = self.linspace(n_fine) if u is None else u.to(self.device, torch.float32).contiguous()
+        return torch.ops.vanerf_b200.importance_sample(self.handle, contrib, z, u)
 
     def query_points(self, tar, pts, view, query_sdf=None, query_vis=None, precision=L.FP32):
         """VANeRF.query on explicit points: pts, view (N,3).  Returns raw (N,5) = [o0,o1,r,g,b], valid (N,), rgba."""
-        N = pts.shape[0]
         pts = pts.to(self.device, torch.float32).contiguous()
         view = view.to(self.device, torch.float32).contiguous()
-        raw, valid, rgba = self.empty((N, 5)), self.empty((N,), torch.uint8), self.empty((N, 5))
-        if query_sdf is not None:
-            query_sdf = query_sdf.to(self.device, torch.float32).contiguous()
-        if query_vis is not None:
-            query_vis = query_vis.to(self.device).to(torch.uint8).contiguous()
-        st = self.lib.dll.vanerf_query_points(self.ctx, precision, C.byref(tar), self._ptr(pts), self._ptr(view), N,
-                                              self._ptr(query_sdf), self._ptr(query_vis), self._ptr(raw), self._ptr(valid),
-                                              self._ptr(rgba), self.stream)
-        self.lib.check(self.ctx, st, "vanerf_query_points")
-        return raw, valid, rgba
+        sdf = self.empty((0,)) if query_sdf is None else query_sdf.to(self.device, torch.float32).contiguous()
+        qv = self.empty((0,), torch.uint8) if query_vis is None else query_vis.to(self.device).to(torch.uint8).contiguous()
+        return torch.ops.vanerf_b200.query_points(self.handle, O.pack_target(tar), pts, view, sdf, qv, int(precision))
+
+    def finish(self):
+        """Completion check (synchronises the stream): raises if a tensor-core launch gave up on a bounded wait since the
+        last check, i.e. if results of the bf16 path are invalid (include/vanerf_b200.h: vanerf_tc_check)."""
+        self.lib.check(self.ctx, self.lib.dll.vanerf_tc_check(self.ctx, self.stream), "vanerf_tc_check")
 
     def tc_error(self) -> int:
         """Nonzero when a bounded wait inside a tensor-core kernel gave up (synchronises the device first)."""
@@ -326,12 +301,7 @@ class Renderer:
     def render_rays(self, tar, pix_xy, n_coarse=64, n_fine=64, fine=True, precision=L.FP32):
         """One call for a ray batch: coarse pass, importance sampling, fine pass (src/model.py:1103-1360).
         Returns (R,8) rows [r,g,b,depth,alpha,sdf,0,0] for the coarse and the fine pass."""
-        R = pix_xy.shape[0]
         pix = pix_xy.to(self.device, torch.int32).contiguous()
-        oc = self.empty((R, 8))
-        of = self.empty((R, 8)) if fine else None
-        st = self.lib.dll.vanerf_render_rays(self.ctx, precision, C.byref(tar), self._ptr(pix), R, n_coarse, n_fine, int(fine),
-                                             self._ptr(self.linspace(n_coarse)), self._ptr(self.linspace(n_fine)) if fine else None,
-                                             self._ptr(oc), self._ptr(of), self.stream)
-        self.lib.check(self.ctx, st, "vanerf_render_rays")
-        return oc, of
+        oc, of = torch.ops.vanerf_b200.render_rays(self.handle, O.pack_target(tar), pix, self.linspace(n_coarse), self.linspace(n_fine),
+                                                   bool(fine), int(precision))
+        return oc, (of if fine else None)
