@@ -221,6 +221,114 @@ def measure_dynamic(args, net, F, steps, warmup):
             "gpu_launches": int(net.renderer.launches - l0), "clocks": clk}
 
 
+def measure_train(args, steps, warmup, patch=64):
+    """Workload E (BASELINE.json configs[4]): training step on a 4096-ray batch per GPU (one random 64x64 patch, `fine=True`,
+    `uniform=False`, view dropout, density noise 0.01): forward + backward through the render path (vanerf_b200/train.py: our
+    kernels for sampling / geometry / projection / gathers / compositing incl. their backward, cuBLAS for the dense layers of the
+    unfused graph), L1 coarse (x1) + L1 fine (x10) against a random target, ONE flat-bucket gradient all-reduce over NCCL, Adam
+    (lr 1e-3) on the render-path parameters.  Weak scaling: every rank trains on its own patch.  `value` = rays/s with the frame
+    resident; e2e = the same step from pinned host buffers (H2D of the maps, per-frame setup, step, D2H of the loss)."""
+    import torch
+    import torch.distributed as dist
+    from vanerf_b200 import synthetic, weights
+    from vanerf_b200 import train as T
+    world, rank, local = dist_env()
+    dev = torch.device("cuda", local)
+    inp_host = synthetic.to_torch(synthetic.make_scene(H, W, V))
+    path = T.TrainableRenderPath(weights.init_state_dict(H, W, mode="ref"), dev, rand_noise_std=0.01)
+    opt = torch.optim.Adam(path.parameters(), lr=1e-3)
+    n_params = sum(p.numel() for p in path.parameters())
+    pin = lambda x: x.contiguous().pin_memory()
+    h = dict(img=pin(inp_host["img"]), feat_tex=pin(inp_host["feat_tex"]), g0=pin(inp_host["feat_geo"][0]), g1=pin(inp_host["feat_geo"][1]),
+             fg=pin(inp_host["src_foreground_mask"].to(torch.uint8)))
+    msk = inp_host["src_foreground_mask"][0, 0, 0].bool()              # patch centres: foreground of source view 0 (stand-in for the target mask)
+    rand = T.TrainRandom(1000 + rank, 2000 + rank)
+    target = torch.rand(patch * patch, 3, generator=torch.Generator().manual_seed(rank)).to(dev)
+    cfg = dict(training=True, uniform=False, fine=True, S_c=S_C, S_f=S_F)
+
+    def frame_dev():
+        f = dict(inp_host)
+        f["img"], f["feat_tex"] = h["img"].to(dev, non_blocking=True), h["feat_tex"].to(dev, non_blocking=True)
+        f["feat_geo"] = [h["g0"].to(dev, non_blocking=True), h["g1"].to(dev, non_blocking=True)]
+        f["src_foreground_mask"] = h["fg"].to(dev, non_blocking=True).bool()
+        return f
+
+    frame = frame_dev()
+    path.set_frame(frame)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(e2e):
+        nonlocal frame
+        if e2e:
+            frame = frame_dev()
+            path.set_frame(frame)
+        pix = T.patch_pixels(msk, W, H, patch, patch, rand)
+        loss, _ = T.training_step(path, frame, pix, target, opt, rand, world, **cfg)
+        if e2e:
+            loss_host.copy_(loss.reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = {}
+    for mode in ("resident", "e2e"):
+        for _ in range(warmup):
+            step(mode == "e2e")
+        sync_all()
+        l0 = path.renderer.launches
+        torch.cuda.reset_peak_memory_stats(dev)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            a.record()
+            loss = step(mode == "e2e")
+            b.record()
+        sync_all()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[mode] = (float(t.item()) / steps, path.renderer.launches - l0, float(loss))
+    if rank != 0:
+        return None
+    ms, launches, loss = res["resident"]
+    ms_e, _, _ = res["e2e"]
+    rays = world * patch * patch
+    n_samples = patch * patch * (S_C + S_C + S_F)
+    flops = 3.0 * FLOP_PER_SAMPLE(V) * n_samples                       # forward + backward (dX and dW) of the dense layers, per rank
+    pk = peaks()
+    h2d = sum(x.numel() * x.element_size() for x in h.values())
+    return {"metric": "rays_per_s", "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"E: training step, {patch}x{patch} random patch = {patch * patch} rays per GPU, V=3, 64 coarse + 128 fine evaluations/ray, "
+                                   "uniform=False (stratified jitter), view dropout, density noise 0.01, L1 coarse + 10 L1 fine, backward through the "
+                                   "render path, one flat-bucket NCCL all-reduce of the gradients, Adam lr 1e-3",
+                       "parameters": n_params, "allreduce_bytes": 4 * n_params, "where": "gpu"},
+            "e2e": {"value": rays / (ms_e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "loss": loss, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "roofline": {"kernel": "dense layers of the unfused training graph (cuBLAS fp32 GEMMs, library)", "bound": "tensor",
+                         "achieved": flops / (ms * 1e-3) / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / pk["tf_sust"],
+                         "traffic": None, "note": "whole step time; fp32 SGEMM cannot reach the bf16 tensor peak it is divided by"}}
+
+
+def run_train(args):
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = measure_train(args, args.steps, max(1, min(args.warmup, 2)))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_dynamic(args):
     import torch
     import torch.distributed as dist
@@ -250,7 +358,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     # headline = the bf16-MLP tensor-core path (north star kernel 2); the fp32 path is measured next to it
     ap.add_argument("--precision", default=os.environ.get("VANERF_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--workload", default="B", choices=["B", "C", "D"], help="headline workload of the JSON line (default B; C and D are "
+    ap.add_argument("--workload", default="B", choices=["B", "C", "D", "E"], help="headline workload of the JSON line (default B; C and D are "
                     "also measured as secondary blocks of the default run)")
     ap.add_argument("--frames", type=int, default=64, help="workload D: frames per step (BASELINE.json configs[3]: 64)")
     ap.add_argument("--no-fp32-path", action="store_true", help="skip the secondary fp32-path measurement")
@@ -262,6 +370,8 @@ def main():
         return run_reference(args)
     if args.workload == "D":
         return run_dynamic(args)
+    if args.workload == "E":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist
@@ -466,6 +576,11 @@ def main():
         dres = measure_dynamic(args, net, args.frames, 1, 1)
         if rank == 0:
             line["workload_D"] = dres
+        del net, r
+        torch.cuda.empty_cache()
+        eres = measure_train(args, 2, 1)
+        if rank == 0:
+            line["workload_E"] = eres
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

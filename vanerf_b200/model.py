@@ -7,9 +7,10 @@
 libvanerf_b200.so through `Renderer`; the CNN encoders are outside the path: their feature maps are
 passed in (`feat_geo`, `feat_tex`) or attached with `attach_im_feat(feat_geo=..., feat_tex=...)`.
 
-Supported configuration: batch size 1 (like every reference config), inference (`uniform=True`), 1..4 source
-views (V-generalisation of SURVEY.md Appendix C), any H x W.  The training branch (random patch, stratified jitter,
-density noise, view dropout; src/model.py:804-810,1172-1189,1226-1230) raises NotImplementedError in this revision.
+Supported configuration: batch size 1 (like every reference config), 1..4 source views (3 on the bf16 path;
+V-generalisation of SURVEY.md Appendix C), any H x W.  Inference (`uniform=True`, eval mode) runs the fused kernels.  The
+training branch (`train()`, or `uniform=False`: random patch, stratified jitter, density noise, view dropout, random importance
+samples; src/model.py:804-810,1155-1156,1172-1189,1226-1230,1439-1442) runs the differentiable graph of vanerf_b200/train.py.
 """
 from __future__ import annotations
 
@@ -37,19 +38,39 @@ class VANeRF:
         self.feat_tex = None
         self._frame_key = None
         self._frame_refs = None
+        self._state_dict = None
+        self.train_path = None
+        self.train_out_h = self.train_out_w = int(self.kwargs.get("train_out_h", 64))       # configs/vanerf.json:46-47
 
     # ---------------------------------------------------------------- module-like surface
+    def train(self, mode=True):
+        """Training mode (src/model.py `net.training` paths): `batch_render_pifu_nerf` then runs the differentiable, unfused graph
+        of vanerf_b200/train.py (random patch, stratified jitter, view dropout, density noise, random importance samples; fp32)
+        on `self.train_path`, whose parameters (reference state_dict keys) an optimiser can update.  `eval()` copies the updated
+        parameters back into the packed weights of the fused inference kernels."""
+        if mode:
+            if self._state_dict is None:
+                raise L.VanerfError("load_state_dict before train()")
+            if self.train_path is None:
+                from .train import TrainableRenderPath
+                self.train_path = TrainableRenderPath(self._state_dict, self.device, self.renderer.lib,
+                                                      rand_noise_std=float(self.kwargs.get("rand_noise_std", 0.01)))
+        self.training = bool(mode)
+        return self
+
     def eval(self):
+        if self.training and self.train_path is not None:
+            self.load_state_dict(self.train_path.state_dict_ref())
         self.training = False
         return self
 
-    def train(self, mode=True):
-        if mode:
-            raise NotImplementedError("vanerf_b200: training branch is not part of this revision (SURVEY.md §8 config E)")
-        return self
+    def parameters(self):
+        """Render-path parameters of the training graph (after train())."""
+        return self.train_path.parameters() if self.train_path is not None else iter(())
 
     def load_state_dict(self, state_dict, strict=False):
         self.renderer.load_state_dict(state_dict)
+        self._state_dict = dict(state_dict)
         self._frame_key = None
         return self
 
@@ -139,17 +160,16 @@ class VANeRF:
 
     def importance_sample(self, contrib, z, sample_per_ray, uniform=False):
         """src/model.py:1425-1462 with the reference's argument convention: contrib (1,R,S-2) = contrib[...,1:-1],
-        z (1,R,S-1) = z_mid.  Uniform sampling only (inference)."""
-        if not uniform:
-            raise NotImplementedError("random importance sampling belongs to the training branch")
+        z (1,R,S-1) = z_mid; uniform=False draws one row of uniform random numbers per ray (training)."""
         import ctypes as C
         r = self.renderer
         R, nb = contrib.shape[1], contrib.shape[2]
         D = nb + 2
         ci, zm = contrib[0].to(self.device).float().contiguous(), z[0].to(self.device).float().contiguous()
         zf = r.empty((R, sample_per_ray))
-        st = r.lib.dll.vanerf_importance_mid(r.ctx, r._ptr(ci), r._ptr(zm), R, D, r._ptr(r.linspace(sample_per_ray)),
-                                             sample_per_ray, 0, r._ptr(zf), r.stream)
+        # uniform=False: one row of uniform random numbers per ray (src/model.py:1442), drawn with torch like the reference
+        u = r.linspace(sample_per_ray) if uniform else torch.rand(R, sample_per_ray).to(self.device).contiguous()
+        st = r.lib.dll.vanerf_importance_mid(r.ctx, r._ptr(ci), r._ptr(zm), R, D, r._ptr(u), sample_per_ray, 0 if uniform else 1, r._ptr(zf), r.stream)
         r.lib.check(r.ctx, st, "vanerf_importance_mid")
         return zf[None]
 
@@ -181,15 +201,14 @@ class VANeRF:
     @staticmethod
     def batch_render_pifu_nerf(net, img_in, cam_in, hand_type, targets, n_views, cam_tar, level=2, stride=0, tar_img=None,
                                feat_geo=None, feat_tex=None, mano_vert_world=None, sp_data={}, objcenter=None, **config):
-        if net.training:
-            raise NotImplementedError("training branch (random patch / stratified sampling) is not part of this revision")
         assert cam_tar["K"].shape[0] == 1, "batch size 1"
         S_c, S_f = config.get("sample_per_ray_c", 64), config.get("sample_per_ray_f", 64)
         fine = config.get("fine", False)
-        if not config.get("uniform", False):
-            raise NotImplementedError("uniform=False (stratified jitter) belongs to the training branch")
         feat_geo = feat_geo if feat_geo is not None else net.feat_geo
         feat_tex = feat_tex if feat_tex is not None else net.feat_tex
+        if net.training or not config.get("uniform", False):
+            return net._batch_render_train(img_in, cam_in, hand_type, targets, n_views, cam_tar, level, stride, tar_img, feat_geo, feat_tex,
+                                           sp_data, **config)
         width, height = int(cam_tar.get("width", cam_in["width"])), int(cam_tar.get("height", cam_in["height"]))
         step = 2 ** (level - 1)
         assert width % step == 0 and height % step == 0
@@ -228,6 +247,48 @@ class VANeRF:
             im = img_in.to(dev)[::n_views].reshape(1, 3, -1)
             out["img_in"] = torch.gather(im, 2, index[None, None].expand(-1, 3, -1)).view(1, 3, out_h, out_w)
         out["vert_vis"] = vert_vis[:, :, None]
+        return out
+
+    def _batch_render_train(self, img_in, cam_in, hand_type, targets, n_views, cam_tar, level, stride, tar_img, feat_geo, feat_tex, sp_data,
+                            **config):
+        """Training flavour of batch_render_pifu_nerf (src/model.py:1103-1422 with net.training / uniform=False): differentiable
+        outputs from vanerf_b200.train.TrainableRenderPath.  config["rand"]: optional `TrainRandom` (seeded parity runs)."""
+        from .train import TrainRandom, patch_pixels
+        if self.train_path is None:
+            self.train(self.training)
+            if self.train_path is None:
+                from .train import TrainableRenderPath
+                self.train_path = TrainableRenderPath(self._state_dict, self.device, self.renderer.lib)
+        path = self.train_path
+        path.rand_noise_std = float(config.get("rand_noise_std", 0.0)) if self.training or "rand_noise_std" in config else 0.0
+        rand = config.get("rand") or TrainRandom()
+        width, height = int(cam_tar.get("width", cam_in["width"])), int(cam_tar.get("height", cam_in["height"]))
+        if self.training and "msk" in config:
+            out_h, out_w = self.train_out_h, self.train_out_w
+            grids = patch_pixels(config["msk"][0].squeeze().bool().cpu(), width, height, out_h, out_w, rand)
+        else:
+            step = 2 ** (level - 1)
+            sx, sy = (int(stride.reshape(-1, 2)[0, 0]), int(stride.reshape(-1, 2)[0, 1])) if isinstance(stride, torch.Tensor) else (int(stride),) * 2
+            out_w, out_h = width // step, height // step
+            ys, xs = torch.meshgrid(torch.arange(0, height, step), torch.arange(0, width, step), indexing="ij")
+            grids = torch.stack([xs + sx, ys + sy], -1).reshape(-1, 2)
+        frame = dict(img=img_in, cam_in=cam_in, targets=targets, sp_data=sp_data, feat_geo=feat_geo, feat_tex=feat_tex,
+                     src_foreground_mask=config["src_foreground_mask"])
+        path.set_frame(frame)
+        o = path.render(cam_tar, config["bounds"], grids, rand=rand, training=self.training, uniform=bool(config.get("uniform", False)),
+                        fine=bool(config.get("fine", False)), S_c=config.get("sample_per_ray_c", 64), S_f=config.get("sample_per_ray_f", 64),
+                        znear=cam_tar.get("znear", cam_in["znear"]), zfar=cam_tar.get("zfar", cam_in["zfar"]))
+        img = lambda t, c: t.reshape(out_h, out_w, c).permute(2, 0, 1)[None]
+        out = {"tex_fg": img(o["tex_fg"], 3), "depth": o["depth"].reshape(1, out_h, out_w), "alpha": o["alpha"].reshape(1, out_h, out_w)}
+        if "tex_fg_fine" in o:
+            out.update({"tex_fg_fine": img(o["tex_fg_fine"], 3), "depth_fine": o["depth_fine"].reshape(1, out_h, out_w),
+                        "alpha_fine": o["alpha_fine"].reshape(1, out_h, out_w), "sdf": o["sdf"].reshape(1, out_h, out_w)})
+        index = (grids[:, 0] + grids[:, 1] * width).long().to(self.device)
+        with torch.no_grad():
+            if tar_img is not None:
+                t = tar_img.reshape(*tar_img.shape[:2], -1).to(self.device)
+                out["tar_img"] = torch.gather(t, 2, index[None, None].expand(t.shape[0], 3, -1)).view(t.shape[0], 3, out_h, out_w)
+        out["vert_vis"] = path.vert_vis[:, :, None]
         return out
 
     # ---------------------------------------------------------------- render_pifu_nerf (src/model.py:1027-1100)
