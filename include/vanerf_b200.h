@@ -102,6 +102,14 @@ typedef struct {
     float bounds[6];     /* config["bounds"] (2,3): min xyz, max xyz (offset +-0.01 applied inside) :1216 */
 } vanerf_target;
 
+/* Per-frame TexVisFusion convolution stacks (src/networks.py:238-262), DEVICE pointers, fp32, reference layouts:
+ * conv0 / conv3 = the two bias-free convolutions, ln1 / ln4 = LayerNorm affine maps.
+ *   img (fconv4): conv0 (21,3,3,3),  ln1 (H,W),   conv3 (42,21,3,3),   ln4 (H,W)
+ *   tex (fconv3): conv0 (21,8,3,3),  ln1 (h,w),   conv3 (42,21,3,3),   ln4 (h,w)
+ *   gt (fconv_gt): conv0 (779,42,3), ln1 (18),    conv3 (1558,779,3),  ln4 (18) */
+typedef struct { const float *conv0, *ln1_w, *ln1_b, *conv3, *ln4_w, *ln4_b; } vanerf_conv_stack;
+typedef struct { vanerf_conv_stack img, tex, gt; } vanerf_gfeat_weights;
+
 int  vanerf_ctx_create(vanerf_ctx** out, int device);
 void vanerf_ctx_destroy(vanerf_ctx* ctx);
 const char* vanerf_status_str(int status);
@@ -117,6 +125,12 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream);
  * (src/networks.py:83,96,270-279), camera-space keypoints (src/spatial.py:74-84), triangle / vertex BVHs.
  * vert_vis_out: optional dev (V,n_verts) fp32 copy of the visibility table. */
 int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_out, void* stream);
+
+/* TexVisFusion global vertex feature of one frame (src/networks.py:273-279: fconv4(img), fconv3(feat_tex) -> (42,18) ->
+ * fconv_gt) as kernels: img dev (V,3,H,W), tex dev (V,8,th,tw) -> out dev (V,1558,18), the `vert_gfeat` input of
+ * vanerf_frame_setup.  LayerNorm shapes follow the map sizes. */
+int vanerf_global_vertex_feature(vanerf_ctx* ctx, const vanerf_gfeat_weights* w, const float* img, const float* tex, int32_t n_views,
+                                 int32_t height, int32_t width, int32_t tex_h, int32_t tex_w, float* out, void* stream);
 
 /* Ray generation, box clip, coarse depths (src/model.py:1190-1238, :1497-1570).
  * pix_xy dev (R,2) int32 target pixels; ztab dev (S) = linspace(0,1,S); rays dev (R,8) out; z dev (R,S) out. */

@@ -43,6 +43,14 @@ class VFrame(C.Structure):
                 ("vert_gfeat", C.c_void_p)]
 
 
+class VConvStack(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv0", "ln1_w", "ln1_b", "conv3", "ln4_w", "ln4_b")]
+
+
+class VGfeatWeights(C.Structure):
+    _fields_ = [("img", VConvStack), ("tex", VConvStack), ("gt", VConvStack)]
+
+
 class VTarget(C.Structure):
     _fields_ = [("inv_K", C.c_float * 9), ("R", C.c_float * 9), ("cam_pos", C.c_float * 3),
                 ("znear", C.c_float), ("zfar", C.c_float), ("bounds", C.c_float * 6)]
@@ -59,6 +67,7 @@ PROTOTYPES = {
     "vanerf_sm_count": (C.c_int, [_P]),
     "vanerf_load_weights": (C.c_int, [_P, C.POINTER(VWeights), _P]),
     "vanerf_frame_setup": (C.c_int, [_P, C.POINTER(VFrame), _P, _P]),
+    "vanerf_global_vertex_feature": (C.c_int, [_P, C.POINTER(VGfeatWeights), _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "vanerf_sample_rays": (C.c_int, [_P, C.POINTER(VTarget), _P, _I, _P, _I, _P, _P, _P]),
     "vanerf_sample_rays_t": (C.c_int, [_P, C.POINTER(VTarget), _P, _I, _P, _I, _I, _P, _P, _P]),
     "vanerf_geom_query": (C.c_int, [_P, C.POINTER(VTarget), _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -14,7 +14,9 @@
 #include "common.cuh"
 
 #define BVH_MAX_NODES 2048
-#define BVH_BUILD_THREADS 512
+#define BVH_BUILD_THREADS 1024
+#define BVH_MAX_PRIMS 4096              // primitives per tree (sort keys are staged in shared memory)
+#define BVH_SLAB_MAX_PRIMS 256          // nodes with more triangles get no slab bound (their slabs are too thick to prune anything)
 
 struct BvhBuildArgs {
     const float* verts;        // (Nv,3)
@@ -24,7 +26,7 @@ struct BvhBuildArgs {
     int* prims;                // out: primitive ids in leaf order
     int2* node_range;          // out: (first, count) of every node
     int* n_nodes;              // out
-    // scratch, context-owned: box 6n floats, cen 3n floats, key n floats, prim_b n, node_a n, node_b n ints,
+    // scratch, context-owned: box 6n floats, cen 3n floats, key n floats (unused since the keys moved to shared memory), prim_b n, node_a n, node_b n ints,
     // nb 12 * BVH_MAX_NODES ints, axis BVH_MAX_NODES ints, active 2 * BVH_MAX_NODES ints
     float* box; float* cen; float* key;
     int* prim_b; int* node_a; int* node_b; int* nb; int* axis; int* active;
@@ -38,6 +40,9 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
     const BvhBuildArgs A = blockIdx.x ? A1 : A0;
     const int tid = threadIdx.x, nt = blockDim.x, n = A.n;
     __shared__ int s_nodes, s_active, s_next;
+    __shared__ int s_scan[32];
+    __shared__ float s_key[BVH_MAX_PRIMS];             // this level's sort key and primitive id per position
+    __shared__ int s_prim[BVH_MAX_PRIMS];
     // ---- primitive boxes and centroids
     for (int i = tid; i < n; i += nt) {
         float mn[3], mx[3];
@@ -74,16 +79,40 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
             for (int c = 0; c < 3; ++c) { b[c] = 0x7fffffff; b[3 + c] = (int)0x80000000; b[6 + c] = 0x7fffffff; b[9 + c] = (int)0x80000000; }
         }
         __syncthreads();
-        for (int i = tid; i < n; i += nt) {
-            const int nd = nodeof[i];
-            if (nd < 0) continue;                  // position belongs to a finished leaf
-            const int p = prims[i];
+        for (int i0 = 0; i0 < n; i0 += nt) {           // uniform trip count: the warp votes / shuffles below need every lane
+            const int i = i0 + tid;
+            const int nd = i < n ? nodeof[i] : -1;     // -1: past the end, or the position belongs to a finished leaf
+            int lo[6], hi[6];                          // ordered-int box min / centroid min, box max / centroid max
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { lo[c] = 0x7fffffff; hi[c] = (int)0x80000000; }
+            if (nd >= 0) {
+                const int p = prims[i];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = bvh_f2o(A.box[6 * p + c]); hi[c] = bvh_f2o(A.box[6 * p + 3 + c]);
+                    lo[3 + c] = hi[3 + c] = bvh_f2o(A.cen[3 * p + c]);
+                }
+            }
+            // node ranges are contiguous, so on the upper levels a whole warp works on one node: reduce in the warp and issue
+            // 12 atomics per warp instead of 12 per primitive (the root alone would serialise 37 000 atomics on 12 addresses)
+            const int nd0 = __shfl_sync(0xffffffffu, nd, 0);
+            const bool uni = __ballot_sync(0xffffffffu, nd == nd0) == 0xffffffffu;
+            if (uni) {
+                if (nd0 < 0) continue;
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                        hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+                    }
+                if ((tid & 31) != 0) continue;
+            } else if (nd < 0) continue;
             int* b = A.nb + 12 * nd;
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
-                atomicMin(&b[c], bvh_f2o(A.box[6 * p + c]));
-                atomicMax(&b[3 + c], bvh_f2o(A.box[6 * p + 3 + c]));
-                atomicMin(&b[6 + c], bvh_f2o(A.cen[3 * p + c]));
-                atomicMax(&b[9 + c], bvh_f2o(A.cen[3 * p + c]));
+                atomicMin(&b[c], lo[c]); atomicMax(&b[3 + c], hi[c]);
+                atomicMin(&b[6 + c], lo[3 + c]); atomicMax(&b[9 + c], hi[3 + c]);
             }
         }
         __syncthreads();
@@ -110,42 +139,66 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
             A.nodes[2 * nd + 1] = mx;
         }
         __syncthreads();
-        // ---- children of the splitting nodes, numbered in the order of the active list (deterministic)
-        if (tid == 0) {
-            int nn = s_nodes, nx = 0;
-            for (int k = 0; k < na; ++k) {
-                const int nd = act[k];
-                if (A.axis[nd] < 0) continue;
+        // ---- children of the splitting nodes, numbered in the order of the active list (deterministic): block-wide exclusive
+        // scan of the split flags (one active node per thread; a level never has more than BVH_BUILD_THREADS nodes)
+        {
+            const int k = tid;
+            const int nd = k < na ? act[k] : -1;
+            const int flag = (nd >= 0 && A.axis[nd] >= 0) ? 1 : 0;
+            int incl = flag;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += t;
+            }
+            if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                const int wtot = tid < (nt >> 5) ? s_scan[tid] : 0;
+                int winc = wtot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, winc, o);
+                    if (tid >= o) winc += t;
+                }
+                s_scan[tid] = winc - wtot;                     // exclusive prefix of the warp totals
+                if (tid == 31) s_next = 2 * winc;              // children created on this level
+            }
+            __syncthreads();
+            if (flag) {
+                const int rank = s_scan[tid >> 5] + incl - 1;  // splitting nodes before this one
                 const int2 rg = A.node_range[nd];
-                const int mid = rg.y / 2, l = nn, r = nn + 1;
-                nn += 2;
+                const int mid = rg.y / 2, l = s_nodes + 2 * rank, r = l + 1;
                 float4 mn = A.nodes[2 * nd], mx = A.nodes[2 * nd + 1];
                 mn.w = __int_as_float(l); mx.w = __int_as_float(r);
                 A.nodes[2 * nd] = mn; A.nodes[2 * nd + 1] = mx;
                 A.node_range[l] = make_int2(rg.x, mid);
                 A.node_range[r] = make_int2(rg.x + mid, rg.y - mid);
-                act_o[nx++] = l; act_o[nx++] = r;
+                act_o[2 * rank] = l; act_o[2 * rank + 1] = r;
             }
-            s_nodes = nn; s_next = nx;
         }
-        // ---- sort key of every live position on its node's axis
+        // ---- sort key of every live position on its node's axis, staged in shared memory with the primitive ids
         for (int i = tid; i < n; i += nt) {
             const int nd = nodeof[i];
             const int ax = nd < 0 ? -1 : A.axis[nd];
-            A.key[i] = ax < 0 ? 0.0f : A.cen[3 * prims[i] + ax];
+            const int p = prims[i];
+            s_prim[i] = p;
+            s_key[i] = ax < 0 ? 0.0f : A.cen[3 * p + ax];
         }
         __syncthreads();
-        // ---- exact rank inside the node's range -> new position; lower half goes to the left child
+        // ---- exact rank inside the node's range -> new position; lower half goes to the left child.  A warp's positions mostly
+        // share one node, so the shared-memory reads of the inner loop are broadcasts.
         for (int i = tid; i < n; i += nt) {
             const int nd = nodeof[i];
-            const int me = prims[i];
+            const int me = s_prim[i];
             if (nd < 0 || A.axis[nd] < 0) { prims_o[i] = me; nodeof_o[i] = -1; continue; }
             const int2 rg = A.node_range[nd];
-            const float c = A.key[i];
+            const float c = s_key[i];
             int rank = 0;
+#pragma unroll 8
             for (int j = rg.x; j < rg.x + rg.y; ++j) {
-                const float cj = A.key[j];
-                rank += (cj < c || (cj == c && prims[j] < me)) ? 1 : 0;
+                const float cj = s_key[j];
+                rank += (cj < c || (cj == c && s_prim[j] < me)) ? 1 : 0;
             }
             const int l = __float_as_int(A.nodes[2 * nd].w), r = __float_as_int(A.nodes[2 * nd + 1].w);
             prims_o[rg.x + rank] = me;
@@ -155,7 +208,7 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
         { int* t = prims; prims = prims_o; prims_o = t; }
         { int* t = nodeof; nodeof = nodeof_o; nodeof_o = t; }
         { int* t = act; act = act_o; act_o = t; }
-        if (tid == 0) { s_active = s_next; s_next = 0; }
+        if (tid == 0) { s_nodes += s_next; s_active = s_next; s_next = 0; }
         __syncthreads();
     }
     if (prims != A.prims)
@@ -224,6 +277,10 @@ __global__ void k_tri_node_bounds(const float* __restrict__ verts, const int* __
     const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= *n_nodes) return;
     const int2 rg = node_range[w];
+    if (rg.y > BVH_SLAB_MAX_PRIMS) {               // upper levels: no slab bound (h = 0 < t, radial distance < r: never prunes)
+        if (lane == 0) { lb[2 * w] = make_float4(0.f, 0.f, 0.f, 3.0e38f); lb[2 * w + 1] = make_float4(0.f, 0.f, 0.f, 3.0e38f); }
+        return;
+    }
     double an[3] = {0, 0, 0}, cs[3] = {0, 0, 0};
     for (int k = rg.x + lane; k < rg.x + rg.y; k += 32) {
         const int f = prims[k];

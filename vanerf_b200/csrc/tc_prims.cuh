@@ -3,7 +3,7 @@
 // Spelling of the PTX follows the CUTLASS 4.x sm100 headers (cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp,
 // tmem_allocator_sm100.hpp, cutlass/arch/barrier.h); nothing here depends on CUTLASS.
 //
-// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_BUDGET_NS of wall time raises the CTA-wide abort flag,
+// Every blocking wait is bounded: a wait that does not complete within TC_WAIT_TRIES tries raises the CTA-wide abort flag,
 // after which all waits fall through, the kernel drains (garbage results), frees TMEM and the host reports an error.
 // A protocol bug therefore costs a wrong answer and an error code, never a hung GPU.
 #pragma once
@@ -29,7 +29,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // One try_wait: suspends the warp in hardware until the phase completes or the suspend-time hint (ns) runs out, so a
 // waiting warp does not burn issue slots polling.
 #define TC_WAIT_HINT_NS 20000u
-#define TC_WAIT_BUDGET_NS 2000000000ull   // a wait gives up after 2 s of wall time (globaltimer), however the suspend hint is honoured
+// A wait gives up after TC_WAIT_TRIES tries: ~21 s when the suspend-time hint is honoured in full, ~0.1 s when every try
+// returns at once (~150 cycles per try); legitimate waits of these kernels are below a millisecond, so neither time slicing,
+// MPS nor a debugger stretching or shortening the tries can trip the bound, and a protocol bug still ends in seconds.
+// (Measured, round 2: a wall-clock bound - globaltimer read on every failed try, or once per 1024 tries with the start time
+// kept in registers - costs k_mlp_tc 7 % and 20 %: the extra live state at ~150 inlined wait sites changes the code of the
+// fast path.  A try count costs one loop counter.)
+#define TC_WAIT_TRIES (1 << 20)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -41,28 +47,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Returns false when the wait was abandoned (time budget spent, or the abort flag raised by another thread).
+// Returns false when the wait was abandoned (try budget spent, or the abort flag raised by another thread).
 // abort_flag[0] = code of the first wait that gave up, abort_flag[1 + code / 100] = last code of each wait class that
-// was still pending.  The clock is only read after a try has failed (a try suspends the warp for up to the hint), i.e. off
-// the fast path; the bound is wall time, so time slicing, MPS or a debugger stretching the tries cannot trip it early.
+// was still pending.
 // (Measured: pure polling with mbarrier.test_wait instead of the suspending try_wait changes nothing, and moving the
 // retry loop out of line does not pay either.)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag, int code) {
-    unsigned long long t0 = 0;
 #pragma unroll 1
-    for (uint32_t it = 1;; ++it) {
+    for (int it = 0; it < TC_WAIT_TRIES; ++it) {
         if (mbar_try_wait(bar, parity)) return true;
         if (*abort_flag) break;           // only reached when a try returned without completion, i.e. off the fast path
-        if ((it & 1023u) == 0) {          // the clock is read once per 1024 failed tries (reading it on every try delayed the
-            const unsigned long long now = globaltimer_ns();      // retry and cost 7 % of k_mlp_tc)
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > TC_WAIT_BUDGET_NS) break;
-        }
     }
     if (*abort_flag == 0) *abort_flag = code;
     abort_flag[1 + code / 100] = code;

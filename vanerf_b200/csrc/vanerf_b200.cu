@@ -17,6 +17,7 @@
 #include "train.cuh"
 #ifndef VANERF_HOST_EMUL
 #include "mlp_tc.cuh"
+#include "gfeat.cuh"
 #endif
 
 struct DevBuf {
@@ -49,7 +50,7 @@ struct vanerf_ctx {
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
     int tc_waves = 8;
-    DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux;
+    DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux, gf_scratch;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
     int* tc_err_dev = nullptr;
@@ -171,7 +172,7 @@ void vanerf_ctx_destroy(vanerf_ctx* c) {
     if (!c) return;
     DeviceGuard dg_(c);
 #ifndef VANERF_HOST_EMUL
-    DevBuf* tcb[] = {&c->tcw, &c->tctab, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux};
+    DevBuf* tcb[] = {&c->tcw, &c->tctab, &c->geo0b, &c->geo1b, &c->texb, &c->T64b, &c->T8b, &c->Ttexb, &c->tc_rec, &c->tc_aux, &c->gf_scratch};
     for (DevBuf* b : tcb) if (b->p) cudaFree(b->p);
     if (c->tc_err_host) cudaFreeHost(c->tc_err_host);
 #endif
@@ -334,7 +335,7 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
     ENSURE(ctx, ctx->tri_node_lb, (size_t)BVH_MAX_NODES * 32);
     ENSURE(ctx, ctx->xyz_ndc, (size_t)V * Nv * 12); ENSURE(ctx, ctx->xy11, (size_t)V * Nv * 8);
     ENSURE(ctx, ctx->zbuf, (size_t)V * RASTER_S * RASTER_S * 8);
-    if (F > 4 * BVH_MAX_NODES || Nv > 8 * BVH_MAX_NODES) return ctx_invalid(ctx, "mesh too large for the per-frame BVH builder");
+    if (F > BVH_MAX_PRIMS || Nv > BVH_MAX_PRIMS) return ctx_invalid(ctx, "mesh too large for the per-frame BVH builder (4096 primitives per tree)");
 
     fr.geo0 = (const float*)ctx->geo0.p; fr.geo1 = (const float*)ctx->geo1.p; fr.tex = (const float*)ctx->tex.p;
     fr.imgm = (const float*)ctx->imgm.p;
@@ -371,7 +372,6 @@ int vanerf_frame_setup(vanerf_ctx* ctx, const vanerf_frame* f, float* vert_vis_o
         }
         // leaf sizes from sweeps on B200 (2/4/8/16 triangles with the per-triangle lower bound x 4/8/16 vertices)
         ba[0].leaf = 8; ba[1].leaf = 16;
-        if (const char* e = getenv("VANERF_TRI_LEAF")) ba[0].leaf = std::max(1, std::min(32, atoi(e)));       // developer override
         VANERF_LAUNCH(k_bvh_build, 2, BVH_BUILD_THREADS, 0, stream, ba[0], ba[1]); CHECK_LAUNCH(ctx);
         VANERF_LAUNCH(k_tri_records, cdiv(F, 128), 128, 0, stream, d_verts, d_faces, (const int*)ctx->tri_prims.p, F, (float4*)ctx->tri_rec.p); CHECK_LAUNCH(ctx);
         VANERF_LAUNCH(k_vtx_records, cdiv(Nv, 128), 128, 0, stream, d_verts, (const int*)ctx->vtx_prims.p, Nv, (float4*)ctx->vtx_rec.p); CHECK_LAUNCH(ctx);
@@ -836,6 +836,72 @@ int vanerf_importance_mid(vanerf_ctx* ctx, const float* contrib_inner, const flo
                   u_per_ray, z_fine, (float*)nullptr, (unsigned char*)nullptr);
     CHECK_LAUNCH(ctx);
     return VANERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-frame global feature
+// TexVisFusion global vertex feature (src/networks.py:246-279) as kernels: gfeat.cuh.  All pointers are device pointers.
+int vanerf_global_vertex_feature(vanerf_ctx* ctx, const vanerf_gfeat_weights* w, const float* img, const float* tex, int32_t V, int32_t H,
+                                 int32_t W, int32_t th, int32_t tw, float* out, void* stream_) {
+    DeviceGuard dg_(ctx);
+#ifndef VANERF_HOST_EMUL
+    if (!ctx || !w || !img || !tex || !out || V <= 0 || V > MAXV || H <= 0 || W <= 0 || th <= 0 || tw <= 0) return ctx_invalid(ctx, "vanerf_global_vertex_feature");
+    const vanerf_conv_stack* st3[3] = {&w->img, &w->tex, &w->gt};
+    for (const vanerf_conv_stack* s : st3)
+        if (!s->conv0 || !s->ln1_w || !s->ln1_b || !s->conv3 || !s->ln4_w || !s->ln4_b) return ctx_invalid(ctx, "vanerf_global_vertex_feature: NULL weight");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t HW = (size_t)H * W, hw = (size_t)th * tw;
+    // scratch: stats (4 x V x 42 x 2 doubles) | stat partials (V x blocks x 84 doubles) | pooled img, tex (V,42,9 each) | pooled
+    // partials (chunks x 2 x V,42,9) | mid (V,779,18) | y1 img | y2 img | y1 tex | y2 tex
+    const dim3 gi(cdiv(W, GF_TILE), cdiv(H, GF_TILE), V), gt(cdiv(tw, GF_TILE), cdiv(th, GF_TILE), V);
+    const int nbi = gi.x * gi.y, nbt = gt.x * gt.y;
+    const size_t n_stat = (size_t)4 * V * GF_OUT * 2;
+    size_t off = n_stat * 8;
+    const size_t o_part = off; off += (size_t)V * nbi * 2 * GF_OUT * 8;
+    const size_t o_pi = off; off += (size_t)V * GF_OUT * 9 * 4;
+    const size_t o_pt = off; off += (size_t)V * GF_OUT * 9 * 4;
+    const size_t o_pp = off; off += (size_t)GF_POOL_CHUNKS * V * GF_OUT * 9 * 4;
+    const size_t o_mid = off; off += (size_t)V * NUM_V_HAND * 18 * 4;
+    off = (off + 255) & ~(size_t)255;
+    const size_t o_y1i = off; off += (size_t)V * GF_MID * HW * 4;
+    const size_t o_y2i = off; off += (size_t)V * GF_OUT * HW * 4;
+    const size_t o_y1t = off; off += (size_t)V * GF_MID * hw * 4;
+    const size_t o_y2t = off; off += (size_t)V * GF_OUT * hw * 4;
+    ENSURE(ctx, ctx->gf_scratch, off);
+    unsigned char* q = (unsigned char*)ctx->gf_scratch.p;
+    double* st = (double*)q;
+    double *st1i = st, *st2i = st + (size_t)V * GF_OUT * 2, *st1t = st + (size_t)2 * V * GF_OUT * 2, *st2t = st + (size_t)3 * V * GF_OUT * 2;
+    double* part = (double*)(q + o_part);
+    float *pi = (float*)(q + o_pi), *pt = (float*)(q + o_pt), *pp = (float*)(q + o_pp), *mid = (float*)(q + o_mid);
+    float *y1i = (float*)(q + o_y1i), *y2i = (float*)(q + o_y2i), *y1t = (float*)(q + o_y1t), *y2t = (float*)(q + o_y2t);
+    TimedScope ts(ctx, KCL_SETUP, stream);
+    const int T = GF_TILE * GF_TILE;
+    // per-view statistics: the (V, blocks, 2 C) partials are reduced per view (part rows of view v are contiguous)
+    auto reduce_stats = [&](int nb, int C, double* dst) -> int {
+        k_gf_reduce<double><<<dim3(cdiv(2 * C * 32, 128), V), 128, 0, stream>>>(part, nb, 2 * C, dst);
+        CHECK_LAUNCH(ctx);
+        return VANERF_OK;
+    };
+    const int np = V * GF_OUT * 9;
+    int rc;
+    k_gf_conv3x3<3, GF_MID, false><<<gi, T, 0, stream>>>(img, w->img.conv0, H, W, nullptr, nullptr, nullptr, y1i, part); CHECK_LAUNCH(ctx);
+    if ((rc = reduce_stats(nbi, GF_MID, st1i))) return rc;
+    k_gf_conv3x3<GF_MID, GF_OUT, true><<<gi, T, 0, stream>>>(y1i, w->img.conv3, H, W, st1i, w->img.ln1_w, w->img.ln1_b, y2i, part); CHECK_LAUNCH(ctx);
+    if ((rc = reduce_stats(nbi, GF_OUT, st2i))) return rc;
+    k_gf_norm_pool<<<dim3(GF_OUT, V, GF_POOL_CHUNKS), 256, 0, stream>>>(y2i, GF_OUT, H, W, st2i, w->img.ln4_w, w->img.ln4_b, pp); CHECK_LAUNCH(ctx);
+    k_gf_reduce<float><<<dim3(cdiv(np * 32, 128), 1), 128, 0, stream>>>(pp, GF_POOL_CHUNKS, np, pi); CHECK_LAUNCH(ctx);
+    k_gf_conv3x3<8, GF_MID, false><<<gt, T, 0, stream>>>(tex, w->tex.conv0, th, tw, nullptr, nullptr, nullptr, y1t, part); CHECK_LAUNCH(ctx);
+    if ((rc = reduce_stats(nbt, GF_MID, st1t))) return rc;
+    k_gf_conv3x3<GF_MID, GF_OUT, true><<<gt, T, 0, stream>>>(y1t, w->tex.conv3, th, tw, st1t, w->tex.ln1_w, w->tex.ln1_b, y2t, part); CHECK_LAUNCH(ctx);
+    if ((rc = reduce_stats(nbt, GF_OUT, st2t))) return rc;
+    k_gf_norm_pool<<<dim3(GF_OUT, V, GF_POOL_CHUNKS), 256, 0, stream>>>(y2t, GF_OUT, th, tw, st2t, w->tex.ln4_w, w->tex.ln4_b, pp); CHECK_LAUNCH(ctx);
+    k_gf_reduce<float><<<dim3(cdiv(np * 32, 128), 1), 128, 0, stream>>>(pp, GF_POOL_CHUNKS, np, pt); CHECK_LAUNCH(ctx);
+    k_gf_conv1d_ln<<<cdiv((long long)V * NUM_V_HAND * 32, 128), 128, 0, stream>>>(pi, pt, w->gt.conv0, V, GF_OUT, NUM_V_HAND, w->gt.ln1_w, w->gt.ln1_b, mid); CHECK_LAUNCH(ctx);
+    k_gf_conv1d_ln<<<cdiv((long long)V * 2 * NUM_V_HAND * 32, 128), 128, 0, stream>>>(mid, nullptr, w->gt.conv3, V, NUM_V_HAND, 2 * NUM_V_HAND, w->gt.ln4_w, w->gt.ln4_b, out); CHECK_LAUNCH(ctx);
+    return VANERF_OK;
+#else
+    (void)w; (void)img; (void)tex; (void)V; (void)H; (void)W; (void)th; (void)tw; (void)out; (void)stream_;
+    return ctx_unsupported(ctx, "vanerf_global_vertex_feature needs the CUDA build");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ stage primitives

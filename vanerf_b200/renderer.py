@@ -124,7 +124,7 @@ class Renderer:
         vw.sigmoid_beta = float(folded["sigmoid_beta"][0])
         self.lib.check(self.ctx, self.lib.dll.vanerf_load_weights(self.ctx, C.byref(vw), self.stream), "vanerf_load_weights")
         # per-frame TexVisFusion convolution stacks stay in torch (cuDNN), on the device
-        self.sd = {k: torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v).float().to(self.device)
+        self.sd = {k: torch.as_tensor(np.asarray(v) if not isinstance(v, torch.Tensor) else v).float().to(self.device).contiguous()
                    for k, v in sd.items() if k.startswith(("tex_vis_fusion.fconv3", "tex_vis_fusion.fconv4", "tex_vis_fusion.fconv_gt"))}
         self.sigmoid_beta = max(2e-3, float(folded["sigmoid_beta"][0]))
 
@@ -134,6 +134,25 @@ class Renderer:
         """TexVisFusion global feature per vertex, (V,1558,18) (src/networks.py:273-279).  LayerNorm shapes follow
         the actual map sizes."""
         sd = self.sd
+        if not self.lib.emulated and img.is_cuda and not torch.is_grad_enabled():
+            # product path: the stacks as kernels of the library (csrc/gfeat.cuh); torch below only serves the host-emulation
+            # tests and the differentiable training graph
+            V, _, H, Wd = img.shape
+            img, feat_tex = img.contiguous(), feat_tex.contiguous()
+            w = L.VGfeatWeights()
+            for stack, pre in ((w.img, "tex_vis_fusion.fconv4"), (w.tex, "tex_vis_fusion.fconv3"), (w.gt, "tex_vis_fusion.fconv_gt")):
+                for field, key in (("conv0", ".0.weight"), ("ln1_w", ".1.weight"), ("ln1_b", ".1.bias"), ("conv3", ".3.weight"),
+                                   ("ln4_w", ".4.weight"), ("ln4_b", ".4.bias")):
+                    t = sd[pre + key]
+                    assert t.is_contiguous() and t.dtype == torch.float32
+                    setattr(stack, field, t.data_ptr())
+            assert tuple(sd["tex_vis_fusion.fconv4.1.weight"].shape) == (H, Wd) and tuple(sd["tex_vis_fusion.fconv3.1.weight"].shape) == tuple(feat_tex.shape[-2:]), \
+                "LayerNorm maps of the per-frame stacks must match the image / texture map sizes"
+            out = self.empty((V, NUM_VERT, 18))
+            st = self.lib.dll.vanerf_global_vertex_feature(self.ctx, C.byref(w), self._ptr(img), self._ptr(feat_tex), V, H, Wd, feat_tex.shape[2],
+                                                           feat_tex.shape[3], self._ptr(out), self.stream)
+            self.lib.check(self.ctx, st, "vanerf_global_vertex_feature")
+            return out
         # cuDNN would take TF32 for these convolutions by default (the reference's own GPU run does, SURVEY.md B-14);
         # the CPU oracle is the arbiter, so the per-frame stacks run in true fp32.
         with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True, allow_tf32=False):

@@ -94,6 +94,13 @@ class CompositeFn(torch.autograd.Function):
         return None, d_rgba, None, None, d_beta
 
 
+def fp32_exact():
+    """Context for forward AND backward of the training graph: cuDNN / cuBLAS in true fp32 (no TF32), deterministic algorithms.
+    The reference's own GPU run takes TF32 for its convolutions; the CPU oracle is the arbiter here.  The
+    backward of a convolution reads these flags when it RUNS, so `loss.backward()` belongs inside the context too."""
+    return torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True, allow_tf32=False)
+
+
 # ---------------------------------------------------------------------------------------------------- randomness
 class TrainRandom:
     """The random tensors of one training forward, drawn in the reference's order and shapes:
@@ -206,7 +213,7 @@ class TrainableRenderPath(torch.nn.Module):
             T64 = FeatSampleFn.apply(r, self.g0, self.vert_xy)
             T8 = FeatSampleFn.apply(r, self.g1, self.vert_xy)
             sd = {k: self.P(k) for k in self._names if k.startswith(("tex_vis_fusion.fconv3", "tex_vis_fusion.fconv4", "tex_vis_fusion.fconv_gt"))}
-            with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True, allow_tf32=False):
+            with fp32_exact():
                 gf = Renderer._global_vertex_feature(self.img, self.tex, sd)
             Tt = torch.cat([FeatSampleFn.apply(r, self.img, self.vert_xy), FeatSampleFn.apply(r, self.tex, self.vert_xy), gf], 2)
             self._tables = (T64, T8, Tt)
@@ -382,7 +389,8 @@ def training_step(path: TrainableRenderPath, frame: Dict, pix_xy: torch.Tensor, 
     loss = lambda_c * (out["tex_fg"] - tgt).abs().mean()
     if "tex_fg_fine" in out:
         loss = loss + lambda_f * (out["tex_fg_fine"] - tgt).abs().mean()
-    loss.backward()
+    with fp32_exact():
+        loss.backward()
     allreduce_gradients(path.parameters(), world)
     if optimizer is not None:
         optimizer.step()
