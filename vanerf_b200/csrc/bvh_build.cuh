@@ -6,8 +6,9 @@
 //
 // Tree = median split on the longest axis of the centroid bounds, top down, one level per iteration, one CTA per tree
 // (3108 triangles / 1558 vertices: the whole build is a few dozen microseconds and needs no host round trip).  The split of
-// a node is an exact rank selection inside its contiguous range (key = centroid coordinate, ties by primitive index), so
-// the node ranges are a deterministic function of the mesh.
+// a node is the exact median of its contiguous range in the order (centroid coordinate, primitive index) - one shared-memory
+// bitonic sort of all primitives per level, range start as the leading key field - so the node ranges are a deterministic
+// function of the mesh.
 // Node = 2 x float4 {min.xyz, as_float(a)}, {max.xyz, as_float(b)}: inner a / b = children, leaf a = ~first primitive
 // (negative), b = count; primitives are stored in leaf order.
 #pragma once
@@ -37,12 +38,13 @@ __device__ __forceinline__ int bvh_f2o(float f) { const int b = __float_as_int(f
 __device__ __forceinline__ float bvh_o2f(int o) { return __int_as_float(o >= 0 ? o : o ^ 0x7fffffff); }
 
 __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0, BvhBuildArgs A1) {
-    const BvhBuildArgs A = blockIdx.x ? A1 : A0;
+    const BvhBuildArgs& A = blockIdx.x ? A1 : A0;
     const int tid = threadIdx.x, nt = blockDim.x, n = A.n;
     __shared__ int s_nodes, s_active, s_next;
     __shared__ int s_scan[32];
-    __shared__ float s_key[BVH_MAX_PRIMS];             // this level's sort key and primitive id per position
-    __shared__ int s_prim[BVH_MAX_PRIMS];
+    __shared__ unsigned long long s_sort[BVH_MAX_PRIMS];     // per level: (range start, ordered centroid coordinate, primitive id)
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;                               // bitonic network size
     // ---- primitive boxes and centroids
     for (int i = tid; i < n; i += nt) {
         float mn[3], mx[3];
@@ -67,12 +69,12 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
         A.node_range[0] = make_int2(0, n);
     }
     __syncthreads();
-    int* prims = A.prims; int* prims_o = A.prim_b;
-    int* nodeof = A.node_a; int* nodeof_o = A.node_b;
+    int* prims = A.prims;
+    int* nodeof = A.node_a;
     int* act = A.active; int* act_o = A.active + BVH_MAX_NODES;
     for (int level = 0; level < 64; ++level) {
         const int na = s_active;
-        if (na == 0) break;
+        if (na == 0 || na > nt) break;                       // a level never has more than BVH_BUILD_THREADS nodes (leaf >= 8, n <= 4096)
         // ---- bounds of the active nodes: primitive boxes and centroids, min / max through ordered-int atomics
         for (int k = tid; k < na; k += nt) {
             int* b = A.nb + 12 * act[k];
@@ -93,21 +95,23 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
                     lo[3 + c] = hi[3 + c] = bvh_f2o(A.cen[3 * p + c]);
                 }
             }
-            // node ranges are contiguous, so on the upper levels a whole warp works on one node: reduce in the warp and issue
-            // 12 atomics per warp instead of 12 per primitive (the root alone would serialise 37 000 atomics on 12 addresses)
-            const int nd0 = __shfl_sync(0xffffffffu, nd, 0);
-            const bool uni = __ballot_sync(0xffffffffu, nd == nd0) == 0xffffffffu;
-            if (uni) {
-                if (nd0 < 0) continue;
+            // node ranges are contiguous, so the lanes of a warp form runs of equal node id: segmented warp reduction (a lane
+            // absorbs the lane o above it while that lane is in the same run), then only the first lane of every run issues the
+            // 12 atomics - one set per (warp, node) instead of one per primitive (the root alone would otherwise serialise
+            // 37 000 atomics on 12 addresses, the deep levels 37 000 scattered ones each)
+            const int lane = tid & 31;
 #pragma unroll
-                for (int c = 0; c < 6; ++c)
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ndo = __shfl_down_sync(0xffffffffu, nd, o);
+                const bool take = (lane + o < 32) && ndo == nd;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
-                        hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
-                    }
-                if ((tid & 31) != 0) continue;
-            } else if (nd < 0) continue;
+                for (int c = 0; c < 6; ++c) {
+                    const int l2 = __shfl_down_sync(0xffffffffu, lo[c], o), h2 = __shfl_down_sync(0xffffffffu, hi[c], o);
+                    if (take) { lo[c] = min(lo[c], l2); hi[c] = max(hi[c], h2); }
+                }
+            }
+            const int ndp = __shfl_up_sync(0xffffffffu, nd, 1);
+            if (nd < 0 || (lane > 0 && ndp == nd)) continue;      // not the head of a run
             int* b = A.nb + 12 * nd;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -140,10 +144,9 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
         }
         __syncthreads();
         // ---- children of the splitting nodes, numbered in the order of the active list (deterministic): block-wide exclusive
-        // scan of the split flags (one active node per thread; a level never has more than BVH_BUILD_THREADS nodes)
+        // scan of the split flags (one active node per thread)
         {
-            const int k = tid;
-            const int nd = k < na ? act[k] : -1;
+            const int nd = tid < na ? act[tid] : -1;
             const int flag = (nd >= 0 && A.axis[nd] >= 0) ? 1 : 0;
             int incl = flag;
 #pragma unroll
@@ -177,42 +180,48 @@ __global__ void __launch_bounds__(BVH_BUILD_THREADS) k_bvh_build(BvhBuildArgs A0
                 act_o[2 * rank] = l; act_o[2 * rank + 1] = r;
             }
         }
-        // ---- sort key of every live position on its node's axis, staged in shared memory with the primitive ids
-        for (int i = tid; i < n; i += nt) {
-            const int nd = nodeof[i];
-            const int ax = nd < 0 ? -1 : A.axis[nd];
-            const int p = prims[i];
-            s_prim[i] = p;
-            s_key[i] = ax < 0 ? 0.0f : A.cen[3 * p + ax];
-        }
-        __syncthreads();
-        // ---- exact rank inside the node's range -> new position; lower half goes to the left child.  A warp's positions mostly
-        // share one node, so the shared-memory reads of the inner loop are broadcasts.
-        for (int i = tid; i < n; i += nt) {
-            const int nd = nodeof[i];
-            const int me = s_prim[i];
-            if (nd < 0 || A.axis[nd] < 0) { prims_o[i] = me; nodeof_o[i] = -1; continue; }
-            const int2 rg = A.node_range[nd];
-            const float c = s_key[i];
-            int rank = 0;
-#pragma unroll 8
-            for (int j = rg.x; j < rg.x + rg.y; ++j) {
-                const float cj = s_key[j];
-                rank += (cj < c || (cj == c && s_prim[j] < me)) ? 1 : 0;
+        // ---- median split = sort of every splitting node's range by (centroid coordinate on its axis, primitive id): one
+        // bitonic sort of the whole array per level with the range start as the most significant key field, so that ranges
+        // (and the positions of finished leaves, keyed by their own index) stay where they are
+        for (int i = tid; i < np2; i += nt) {
+            unsigned long long key = ~0ull;
+            if (i < n) {
+                const int nd = nodeof[i];
+                const int p = prims[i];
+                const int ax = nd < 0 ? -1 : A.axis[nd];
+                if (ax < 0) key = ((unsigned long long)i << 44) | (unsigned long long)p;
+                else {
+                    const unsigned ukey = (unsigned)bvh_f2o(A.cen[3 * p + ax]) ^ 0x80000000u;
+                    key = ((unsigned long long)A.node_range[nd].x << 44) | ((unsigned long long)ukey << 12) | (unsigned long long)p;
+                }
             }
-            const int l = __float_as_int(A.nodes[2 * nd].w), r = __float_as_int(A.nodes[2 * nd + 1].w);
-            prims_o[rg.x + rank] = me;
-            nodeof_o[rg.x + rank] = rank < rg.y / 2 ? l : r;
+            s_sort[i] = key;
         }
         __syncthreads();
-        { int* t = prims; prims = prims_o; prims_o = t; }
-        { int* t = nodeof; nodeof = nodeof_o; nodeof_o = t; }
+        for (int k = 2; k <= np2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (np2 >> 1); t += nt) {
+                    const int i = ((t / j) * 2 * j) + (t % j), q = i + j;
+                    const unsigned long long x = s_sort[i], y = s_sort[q];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { s_sort[i] = y; s_sort[q] = x; }
+                }
+                __syncthreads();
+            }
+        // ---- new primitive order; the lower half of a split range belongs to the left child
+        for (int i = tid; i < n; i += nt) {
+            const int nd = nodeof[i];
+            prims[i] = (int)(s_sort[i] & 0xfffull);
+            if (nd < 0) continue;
+            if (A.axis[nd] < 0) { nodeof[i] = -1; continue; }
+            const int2 rg = A.node_range[nd];
+            nodeof[i] = (i - rg.x) < rg.y / 2 ? __float_as_int(A.nodes[2 * nd].w) : __float_as_int(A.nodes[2 * nd + 1].w);
+        }
+        __syncthreads();
         { int* t = act; act = act_o; act_o = t; }
         if (tid == 0) { s_nodes += s_next; s_active = s_next; s_next = 0; }
         __syncthreads();
     }
-    if (prims != A.prims)
-        for (int i = tid; i < n; i += nt) A.prims[i] = prims[i];
     if (tid == 0) *A.n_nodes = s_nodes;
 }
 

@@ -49,7 +49,7 @@ struct vanerf_ctx {
     TcTables h_tc;                     // host copy of the biases / small fp32 layers (weights) + camera-space keypoints (frame)
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
-    int tc_waves = 8;
+    int tc_waves = 16;
     DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux, gf_scratch;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
@@ -492,8 +492,8 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         return VANERF_ERR_UNSUPPORTED;
     }
     if (tc_take_error(ctx)) return VANERF_ERR_CUDA;        // an earlier launch gave up: reported once, then the path is usable again
-    // tiles per launch: `tc_waves` tile pairs per CTA (default 8: ~580 MB of operand images per launch at V = 3; one pair per
-    // CTA keeps the images L2 resident but costs eight times the launches, and the gather runs 20 % faster on the larger grid)
+    // tiles per launch: `tc_waves` tile pairs per CTA (default 16: ~1.2 GB of operand images per launch at V = 3; one pair per
+    // CTA keeps the images L2 resident but costs sixteen times the launches, and the gather runs 22 % faster on the larger grid)
     const int max_tiles = TC_TILES * ctx->sm_count * ctx->tc_waves;
     const long long chunk = (long long)max_tiles * TC_ROWS;
     ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * TC_REC_IMAGES * TC_SLOT);
@@ -986,7 +986,9 @@ size_t vanerf_scratch_bytes(const vanerf_ctx* ctx, int32_t R, int32_t S) {
     return N * (4 + 4 + 4 + V + 20 + 4 + 1) + (size_t)R * 32 + (size_t)SHADE_CHUNK * V * REC_STRIDE * 4;
 }
 
-#define RENDER_RAY_CHUNK 8192
+// rays per internal chunk of vanerf_render_rays: 65 536 rays x 128 depths = 8.4 M samples (~0.4 GB of per-sample scratch); with 16 tile
+// pairs per shading launch a 334x512 view is ~140 kernel launches
+#define RENDER_RAY_CHUNK 65536
 
 int vanerf_render_rays(vanerf_ctx* ctx, int precision, const vanerf_target* tar, const int32_t* pix_xy, int32_t R,
                        int32_t Sc, int32_t Sf, int32_t fine, const float* ztab, const float* utab, float* out_coarse,
