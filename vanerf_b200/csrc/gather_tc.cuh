@@ -286,3 +286,77 @@ k_gather_tc(FrameDev fr, FrameTc ft, TargetDev tar, const float* __restrict__ ra
         }   // round
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split-precision ("fp32") path: the fp32 gather records of k_gather (one 308-float row per (sample, view), gather.cuh /
+// common.cuh REC_*) -> the same five operand images as k_gather_tc, each as a bf16 hi image and a bf16 lo image
+// (value = hi + lo to 16 mantissa bits), plus a 96-byte side record whose eight "extras" stay fp32.
+// rec_img: (n_tiles, V, 10, 16 KB) = images R0..R4 hi, then R0..R4 lo; aux: (n_tiles * 128, V, 96 B).
+// One thread per (row, view, image, 16-byte chunk); rows past n_chunk replicate the last sample (never stored).
+// record offset of element j of chunk c of image img (-1 = zero); mirrors the operand layout of k_gather_tc
+__device__ __forceinline__ int rec_split_offset(int img, int c, int j) {
+    switch (img) {
+        case 0: return REC_PX64 + 8 * c + j;
+        case 1: return REC_A64 + 8 * c + j;
+        case 2: return REC_B64 + 8 * c + j;
+        case 3:
+            if (c == 0 || c == 5) return j < 4 ? REC_SDF + j : -1;               // sdf, qvis, vn, vt
+            if (c == 2) return REC_PX8 + j;
+            if (c == 3) return REC_A8 + j;
+            if (c == 4) return REC_B8 + j;
+            return -1;
+        default:
+            if (c == 0) return REC_QTEX + j;
+            if (c == 1) return REC_ATEX + 3 + j;
+            if (c == 2) return REC_BTEX + 3 + j;
+            if (c == 3 || c == 4) return REC_ATEX + 11 + 8 * (c - 3) + j;
+            if (c == 5 || c == 6) return REC_BTEX + 11 + 8 * (c - 5) + j;
+            switch (j) {                                                          // c == 7
+                case 0: return REC_ATEX + 27;
+                case 1: return REC_ATEX + 28;
+                case 2: return REC_BTEX + 27;
+                case 3: return REC_BTEX + 28;
+                case 4: return REC_QIMG;
+                case 5: return REC_QIMG + 1;
+                case 6: return REC_QIMG + 2;
+                default: return REC_ATEX;
+            }
+    }
+}
+__global__ void __launch_bounds__(256) k_rec_split(const float* __restrict__ rec, int V, int n_chunk, unsigned char* __restrict__ rec_img,
+                                                   unsigned char* __restrict__ aux) {
+    __shared__ short tab[TC_REC_IMAGES * 8 * 8];                                // the column map, built once per block: no divergent switches per element
+    for (int k = threadIdx.x; k < TC_REC_IMAGES * 8 * 8; k += blockDim.x) tab[k] = (short)rec_split_offset(k >> 6, (k >> 3) & 7, k & 7);
+    __syncthreads();
+    const int n_rows = ((n_chunk + TC_ROWS - 1) / TC_ROWS) * TC_ROWS;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_row = TC_REC_IMAGES * 8 + 6;                                  // 40 image chunks + 6 float4 of the side record
+    if (t >= (long long)n_rows * V * per_row) return;
+    const int u = (int)(t % per_row);
+    const long long iv = t / per_row;
+    const int v = (int)(iv % V), i = (int)(iv / V);
+    const float* r = rec + ((size_t)(i < n_chunk ? i : n_chunk - 1) * V + v) * REC_STRIDE;
+    if (u < TC_REC_IMAGES * 8) {
+        const int img = u >> 3, c = u & 7;
+        float f[8], fh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int o = tab[8 * u + j]; f[j] = o >= 0 ? r[o] : 0.0f; }
+        const uint4 hi = pack8(f);
+        unpack8(hi, fh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] -= fh[j];
+        const int tile = i / TC_ROWS, row = i % TC_ROWS;
+        unsigned char* base = rec_img + ((size_t)tile * V + v) * (2 * TC_REC_IMAGES * TC_SLOT) + tc::slot_chunk_off(row, c);
+        *reinterpret_cast<uint4*>(base + (size_t)img * TC_SLOT) = hi;
+        *reinterpret_cast<uint4*>(base + (size_t)(TC_REC_IMAGES + img) * TC_SLOT) = pack8(f);
+    } else {
+        const int q = u - TC_REC_IMAGES * 8;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q == 0) o = make_float4(r[REC_CAM], r[REC_CAM + 1], r[REC_CAM + 2], r[REC_RD]);
+        else if (q == 1) o = make_float4(r[REC_RD + 1], r[REC_RD + 2], r[REC_RD + 3], r[REC_PW]);
+        else if (q == 2) o = make_float4(r[REC_MASK], 0.f, 0.f, 0.f);
+        else if (q == 3) o = make_float4(r[REC_ATEX + 1], r[REC_ATEX + 2], r[REC_BTEX], r[REC_BTEX + 1]);
+        else if (q == 4) o = make_float4(r[REC_BTEX + 2], r[REC_QVIS], r[REC_VN], r[REC_VT]);
+        *reinterpret_cast<float4*>(aux + ((size_t)i * V + v) * 96 + 16 * q) = o;
+    }
+}

@@ -49,6 +49,12 @@
 #define TC_SREG 128                      // TMEM columns of the pooling sums S1|S2, later the per-view f (40 each)
 #define TC_SRC 112                       // TMEM columns of the per-view source colours (4 per view)
 #define TC_MAXV 3
+// Split-precision ("fp32") variant of the kernel, template parameter SPLIT: every operand is kept as bf16 hi + bf16 lo
+// (x = hi + lo to 16 mantissa bits) and every K step issues three MMAs (hi*hi + lo*hi + hi*lo; the dropped lo*lo term is
+// 2^-18 relative), accumulating in fp32 in TMEM.  One 128-sample tile per CTA: the second tile's operand slots hold the lo
+// images, the weight ring carries (hi, lo) chunk pairs.  Epilogue functions run in fp32 (no packed-bf16 shortcuts).
+#define TC_LO_OFF (TC_NACT * TC_SLOT)    // byte offset of the lo image of an operand slot (= the other tile's slots)
+#define TC_AUX_BYTES_SPLIT 96            // side record of the split path: the 8 "extras" travel as fp32
 #define TC_OFF_RING (TC_TILES * TC_NACT * TC_SLOT)
 #define TC_OFF_TAB (TC_OFF_RING + TC_NRING * TC_SLOT)
 #if TC_TAB_PARAM
@@ -362,12 +368,14 @@ static inline uint16_t f2bf_host(float f) {
 }
 
 // Builds the step / op / chunk tables and the bf16 weight images (blob) from the folded fp32 layers.
-static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, TcProg& P, std::vector<uint16_t>& blob) {
+static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, TcProg& P, std::vector<uint16_t>& blob,
+                     std::vector<uint16_t>* blob_lo = nullptr) {
     std::vector<std::vector<TcOpSpec>> st;
     tc_build_script(st);
     memset(&T, 0, sizeof(T));
     memset(&P, 0, sizeof(P));
     blob.clear();
+    if (blob_lo) blob_lo->clear();
     int n_ops = 0, n_chunks = 0;
     for (int s = 0; s < ST_COUNT; ++s) {
         P.steps[s].op0 = (uint16_t)n_ops;
@@ -399,12 +407,21 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
             if (o.share) continue;                                               // weights already in the chunk
             const size_t base = blob.size();
             blob.resize(base + bytes / 2, 0);
+            if (blob_lo) blob_lo->resize(base + bytes / 2, 0);
             for (int n = 0; n < L.out_dim; ++n)
                 for (int k = 0; k < ncols; ++k) {
                     const int ki = o.kmap[k];
                     if (ki < 0) continue;
                     const size_t byte = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ n) & 7) << 4) + (k & 7) * 2;
-                    blob[base + byte / 2] = f2bf_host(L.w[(size_t)n * L.in_dim + ki]);
+                    const float wv = L.w[(size_t)n * L.in_dim + ki];
+                    const uint16_t hi = f2bf_host(wv);
+                    blob[base + byte / 2] = hi;
+                    if (blob_lo) {                 // split path: w = hi + lo to 16 mantissa bits
+                        const uint32_t hb = (uint32_t)hi << 16;
+                        float hf;
+                        memcpy(&hf, &hb, 4);
+                        (*blob_lo)[base + byte / 2] = f2bf_host(wv - hf);
+                    }
                 }
             cur_bytes += bytes;
             P.chunks[n_chunks - 1].bytes = cur_bytes;
@@ -501,6 +518,7 @@ struct TcArgs {
     const unsigned char* aux;          // (n_tiles*128, V, 64)
     int V, n_chunk;
     long long sample0;
+    unsigned wblob_lo_off;             // split path: byte offset of the lo weight images inside wblob
     float* rgba;                       // (N,5) or NULL
     float* raw_out;                    // (N,5) or NULL
     float* dbg_latent;                 // (N,128) or NULL
@@ -592,22 +610,30 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
 
 // Issues op I (and the following ones) of step ST: everything but the ring slot of the weight chunk is an immediate.
 // Whole warp, converged; `lead` = the elected lane that executes the MMAs and commits.
-template <int ST, int I>
-__device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint32_t slot_i, TcShared* sh, uint64_t ad_base, uint64_t bd_base,
-                                            uint32_t tmem, bool lead) {
+template <int ST, int I, bool SPLIT>
+__device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint32_t slot_i, uint64_t bd_slot_lo, uint32_t slot_lo, TcShared* sh,
+                                            uint64_t ad_base, uint64_t bd_base, uint32_t tmem, bool lead) {
     constexpr TcStep S = kProg.steps[ST];
     constexpr TcOp op = kProg.ops[S.op0 + I];
     constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
     if (first_in_chunk) {
-        const uint32_t c = cc + op.chunk_rel;
+        const uint32_t c = (SPLIT ? 2u : 1u) * (cc + op.chunk_rel);       // split: logical chunk c = ring chunks 2c (hi), 2c + 1 (lo)
         slot_i = c % TC_NRING;
         bd_slot = bd_base + (uint64_t)(slot_i * (TC_SLOT >> 4));
-#if !TC_PREWAIT
-        TC_PROF(7000);
-        tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
-        tc::tcgen05_fence_after();
-        TC_PROF(7100);
+        if (SPLIT) {
+            slot_lo = (c + 1) % TC_NRING;
+            bd_slot_lo = bd_base + (uint64_t)(slot_lo * (TC_SLOT >> 4));
+        }
+#if TC_PREWAIT
+        if (SPLIT)
 #endif
+        {
+            TC_PROF(7000);
+            tc::mbar_wait(&sh->wfull[slot_i], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
+            if (SPLIT) tc::mbar_wait(&sh->wfull[slot_lo], ((c + 1) / TC_NRING) & 1, sh->abort_flag, 100 + ST);
+            tc::tcgen05_fence_after();
+            TC_PROF(7100);
+        }
     }
     // descriptors = base descriptor + (byte offset >> 4): the start-address field (14 bits of address >> 4) cannot
     // carry into its neighbours because every operand lies inside the CTA's 227 KB of shared memory
@@ -615,11 +641,19 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
     const uint64_t bd = bd_slot + (uint64_t)(op.b_off >> 4);
     if (lead) {
 #pragma unroll
-        for (int k = 0; k < ((TC_ABLATE & 4) ? 1 : op.nk); ++k)              // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
+        for (int k = 0; k < ((TC_ABLATE & 4) ? 1 : op.nk); ++k) {            // +32 bytes (16 bf16) per K step inside the 128-byte swizzled row
             tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd + 2 * k, op.idesc, (op.accum || k > 0) ? 1u : 0u);
-        if (op.last_in_chunk) tc::umma_commit(&sh->wempty[slot_i]);
+            if (SPLIT) {
+                tc::umma_bf16(tmem + op.d_col, ad + (uint64_t)(TC_LO_OFF >> 4) + 2 * k, bd + 2 * k, op.idesc, 1u);                    // lo(A) x hi(W)
+                tc::umma_bf16(tmem + op.d_col, ad + 2 * k, bd_slot_lo + (uint64_t)(op.b_off >> 4) + 2 * k, op.idesc, 1u);             // hi(A) x lo(W)
+            }
+        }
+        if (op.last_in_chunk) {
+            tc::umma_commit(&sh->wempty[slot_i]);
+            if (SPLIT) tc::umma_commit(&sh->wempty[slot_lo]);
+        }
     }
-    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1>(cc, bd_slot, slot_i, sh, ad_base, bd_base, tmem, lead);
+    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1, SPLIT>(cc, bd_slot, slot_i, bd_slot_lo, slot_lo, sh, ad_base, bd_base, tmem, lead);
 }
 // Waits for every weight chunk of step ST (TC_PREWAIT): done BEFORE the wait for the step's operands, because the weights
 // are streamed a step ahead and have normally landed long before the tile's epilogue publishes; the ~100-cycle
@@ -640,12 +674,14 @@ __device__ __forceinline__ void tc_prewait_chunks(uint32_t cc, TcShared* sh) {
 // (and finished reading the accumulators the step overwrites), then issue the step's MMAs and commit.
 // COMMIT: 0 = accumulator barrier, 1..3 = PE ring-slot barrier (COMMIT - 1), -1 = none.
 // cc_base = index of the first weight chunk of this iteration of the step's group (see TcProg::cc_off).
-template <int ST, int COMMIT>
+template <int ST, int COMMIT, bool SPLIT>
 __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, TcShared* sh, uint32_t act_u32, uint32_t ring_u32,
                                                uint32_t tmem, int tg, bool lead) {
 #if TC_PREWAIT
-    constexpr uint32_t cc_off_pre = kProg.cc_off[ST];
-    tc_prewait_chunks<ST, 0>(cc_base + cc_off_pre, sh);
+    if constexpr (!SPLIT) {              // split path: a step's (hi, lo) chunk pairs can exceed the ring, no pre-wait
+        constexpr uint32_t cc_off_pre = kProg.cc_off[ST];
+        tc_prewait_chunks<ST, 0>(cc_base + cc_off_pre, sh);
+    }
 #endif
     TC_PROF(8000 + ST);                  // issuer: previous step issued, waiting for this step's operands
     const bool ok = tc::mbar_wait(&sh->ready[tg][n % TC_NREADY], (n / TC_NREADY) & 1, sh->abort_flag, 600 + ST);
@@ -657,7 +693,7 @@ __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, Tc
     // kernel is draining and results are discarded): otherwise the compiler computes the descriptors of all 140-odd
     // MMAs ahead of the waits and spills them to local memory.
     const uint32_t never = ok ? 0u : 16u;
-    tc_issue_op<ST, 0>(cc_base + cc_off, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead);
+    tc_issue_op<ST, 0, SPLIT>(cc_base + cc_off, 0, 0, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead);
     if (lead) {
         if (COMMIT == 0) tc::umma_commit(&sh->acc_bar[tg]);
         else if (COMMIT > 0) tc::umma_commit(&sh->pfree[tg][COMMIT > 0 ? COMMIT - 1 : 0]);
@@ -712,8 +748,44 @@ struct TcTile {
     __device__ __forceinline__ void st_chunk(int s, int chunk, const uint4& q) const {
         *reinterpret_cast<uint4*>(slot(s) + coff(chunk)) = q;
     }
+    __device__ __forceinline__ void st_chunk_lo(int s, int chunk, const uint4& q) const {
+        *reinterpret_cast<uint4*>(slot(s) + TC_LO_OFF + coff(chunk)) = q;
+    }
     __device__ __forceinline__ uint4 ld_chunk(int s, int chunk) const {
         return *reinterpret_cast<const uint4*>(slot(s) + coff(chunk));
+    }
+    // ---- split-aware operand access: 8 fp32 values <-> one 16-byte chunk (hi image) [+ the same chunk of the lo image]
+    template <bool SPLIT>
+    __device__ __forceinline__ void put8(int s, int chunk, const float (&f)[8]) const {
+        const uint4 hi = pack8(f);
+        st_chunk(s, chunk, hi);
+        if (SPLIT) {
+            float fh[8], lo[8];
+            unpack8(hi, fh);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) lo[i] = f[i] - fh[i];
+            *reinterpret_cast<uint4*>(slot(s) + TC_LO_OFF + coff(chunk)) = pack8(lo);
+        }
+    }
+    template <bool SPLIT>
+    __device__ __forceinline__ void put8(int s, int chunk, float a, float b, float c, float d, float e, float f, float g, float h) const {
+        const float v[8] = {a, b, c, d, e, f, g, h};
+        put8<SPLIT>(s, chunk, v);
+    }
+    template <bool SPLIT>
+    __device__ __forceinline__ void get8(int s, int chunk, float (&f)[8]) const {
+        unpack8(ld_chunk(s, chunk), f);
+        if (SPLIT) {
+            float lo[8];
+            unpack8(*reinterpret_cast<const uint4*>(slot(s) + TC_LO_OFF + coff(chunk)), lo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += lo[i];
+        }
+    }
+    template <bool SPLIT>
+    __device__ __forceinline__ void zero8(int s, int chunk) const {
+        st_chunk(s, chunk, make_uint4(0, 0, 0, 0));
+        if (SPLIT) *reinterpret_cast<uint4*>(slot(s) + TC_LO_OFF + coff(chunk)) = make_uint4(0, 0, 0, 0);
     }
     __device__ __forceinline__ void ld16(int col, float (&v)[16]) const {
         uint32_t r[16];
@@ -762,20 +834,22 @@ struct TcTile {
         TC_PROF(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
-    // multiply the 8 bf16 of a chunk by per-element gates (fp32 product, one rounding back to bf16)
+    // multiply the 8 values of a chunk by per-element gates (fp32 product, one rounding back to bf16 [hi + lo])
+    template <bool SPLIT>
     __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
         float f[8];
-        unpack8(ld_chunk(s, chunk), f);
+        get8<SPLIT>(s, chunk, f);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] *= g[i];
-        st_chunk(s, chunk, pack8(f));
+        put8<SPLIT>(s, chunk, f);
     }
+    template <bool SPLIT>
     __device__ __forceinline__ void gate_chunk1(int s, int chunk, float g) const {
 #if TC_ABLATE & 16
         return;
 #endif
         float f[8];
-        unpack8(ld_chunk(s, chunk), f);
+        get8<SPLIT>(s, chunk, f);
 #if TC_F32X2
         const float2 g2 = make_float2(g, g);
 #pragma unroll
@@ -784,12 +858,13 @@ struct TcTile {
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] *= g;
 #endif
-        st_chunk(s, chunk, pack8(f));
+        put8<SPLIT>(s, chunk, f);
     }
 };
 
 // acc[16 columns in r] + bias -> ACT -> bf16 -> operand chunks `chunk`, `chunk + 1` of the slot at `slot_base`.
-template <int ACT>
+// SPLIT: the activation runs in fp32 and the result is stored as bf16 hi + bf16 lo.
+template <int ACT, bool SPLIT>
 __device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const float* bias, unsigned char* slot_base, const TcTile& t, int chunk) {
     float v[16];
     if (bias) {
@@ -809,14 +884,29 @@ __device__ __forceinline__ void tc_epi_group(const uint32_t (&r)[16], const floa
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
     }
-    *reinterpret_cast<uint4*>(slot_base + t.coff(chunk)) =
-        make_uint4(tc_pack_act<ACT>(v[0], v[1]), tc_pack_act<ACT>(v[2], v[3]), tc_pack_act<ACT>(v[4], v[5]), tc_pack_act<ACT>(v[6], v[7]));
-    *reinterpret_cast<uint4*>(slot_base + t.coff(chunk + 1)) =
-        make_uint4(tc_pack_act<ACT>(v[8], v[9]), tc_pack_act<ACT>(v[10], v[11]), tc_pack_act<ACT>(v[12], v[13]), tc_pack_act<ACT>(v[14], v[15]));
+    if constexpr (SPLIT) {
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = tc_act<ACT>(v[i]); b[i] = tc_act<ACT>(v[8 + i]); }
+        const uint4 ha = pack8(a), hb = pack8(b);
+        float fa[8], fb[8];
+        unpack8(ha, fa); unpack8(hb, fb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] -= fa[i]; b[i] -= fb[i]; }
+        *reinterpret_cast<uint4*>(slot_base + t.coff(chunk)) = ha;
+        *reinterpret_cast<uint4*>(slot_base + t.coff(chunk + 1)) = hb;
+        *reinterpret_cast<uint4*>(slot_base + TC_LO_OFF + t.coff(chunk)) = pack8(a);
+        *reinterpret_cast<uint4*>(slot_base + TC_LO_OFF + t.coff(chunk + 1)) = pack8(b);
+    } else {
+        *reinterpret_cast<uint4*>(slot_base + t.coff(chunk)) =
+            make_uint4(tc_pack_act<ACT>(v[0], v[1]), tc_pack_act<ACT>(v[2], v[3]), tc_pack_act<ACT>(v[4], v[5]), tc_pack_act<ACT>(v[6], v[7]));
+        *reinterpret_cast<uint4*>(slot_base + t.coff(chunk + 1)) =
+            make_uint4(tc_pack_act<ACT>(v[8], v[9]), tc_pack_act<ACT>(v[10], v[11]), tc_pack_act<ACT>(v[12], v[13]), tc_pack_act<ACT>(v[14], v[15]));
+    }
 }
 // acc[col0 + 16 g .. +16) -> chunks (chunk0 + 2 g, +1), g < N16.  The TMEM load of group g + 1 is in flight while
 // group g is processed.
-template <int ACT, int N16>
+template <int ACT, int N16, bool SPLIT = false>
 __device__ __forceinline__ void tc_epi_store(const TcTile& t, int col0, const float* bias, unsigned char* slot_base, int chunk0) {
     uint32_t ra[16], rb[16];                 // double buffer: a buffer is only read after the wait that follows its load
     tc::tmem_ld16(t.trow + col0, ra);
@@ -824,15 +914,15 @@ __device__ __forceinline__ void tc_epi_store(const TcTile& t, int col0, const fl
     for (int g = 0; g < N16; g += 2) {
         tc::tmem_ld_wait();
         if (g + 1 < N16) tc::tmem_ld16(t.trow + col0 + 16 * (g + 1), rb);
-        tc_epi_group<ACT>(ra, bias ? bias + 16 * g : nullptr, slot_base, t, chunk0 + 2 * g);
+        tc_epi_group<ACT, SPLIT>(ra, bias ? bias + 16 * g : nullptr, slot_base, t, chunk0 + 2 * g);
         if (g + 1 < N16) {
             tc::tmem_ld_wait();
             if (g + 2 < N16) tc::tmem_ld16(t.trow + col0 + 16 * (g + 2), ra);
-            tc_epi_group<ACT>(rb, bias ? bias + 16 * (g + 1) : nullptr, slot_base, t, chunk0 + 2 * (g + 1));
+            tc_epi_group<ACT, SPLIT>(rb, bias ? bias + 16 * (g + 1) : nullptr, slot_base, t, chunk0 + 2 * (g + 1));
         }
     }
 }
-#define EPI(ACT, col0, n16, bias, s, chunk0) tc_epi_store<ACT, n16>(t, (col0), (bias), t.slot(s), (chunk0))
+#define EPI(ACT, col0, n16, bias, s, chunk0) tc_epi_store<ACT, n16, SPLIT>(t, (col0), (bias), t.slot(s), (chunk0))
 #define BIASP(l) (t.tb->bias + t.tb->bias_off[l])          // bias offsets are multiples of 16 floats
 #define NOBIAS ((const float*)nullptr)
 
@@ -938,24 +1028,16 @@ __device__ __forceinline__ void tc_load_step_dyn(int st, uint32_t& cc, unsigned 
 // table lookups there even though the unrolled code is cold.)
 // MMA issuer warp of tile group TG (whole warp, converged).  TG is a template parameter and every counter derives from
 // kernel parameters and block indices, so that the compiler keeps the whole address arithmetic on the uniform datapath.
-#ifndef TC_ISSUER_SHARED
-#define TC_ISSUER_SHARED 1               // 1: both issuer warps run ONE copy of the (fully unrolled, ~60 KB) issue code
-#endif
-#if TC_ISSUER_SHARED
+template <bool SPLIT>
 __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int n_pairs) {
     const int tg = __shfl_sync(0xffffffffu, tg_in, 0);          // warp-uniform: the tile's offsets stay on the uniform datapath
     const int TG = tg;
-#else
-template <int TG>
-__device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs) {
-    constexpr int tg = TG;
-#endif
     const uint32_t act_u32 = tc::smem_u32(tc_smem_raw) + TG * (TC_NACT * TC_SLOT), ring_u32 = tc::smem_u32(tc_smem_raw) + TC_OFF_RING;
     const uint32_t tmem = __shfl_sync(0xffffffffu, sh->tmem_base, 0) + TG * TC_TMEM_TILE;
     const bool lead = tc_elect();
     constexpr uint32_t cc_gm = kProg.cc_gm, cc_q = kProg.cc_q, cc_t = kProg.cc_t, cc_i = kProg.cc_i;
     uint32_t n = 0, cc = 0;
-#define ISTEP(ST, COMMIT) tc_issuer_step<ST, COMMIT>(n, cc, sh, act_u32, ring_u32, tmem, tg, lead)
+#define ISTEP(ST, COMMIT) tc_issuer_step<ST, COMMIT, SPLIT>(n, cc, sh, act_u32, ring_u32, tmem, tg, lead)
 #pragma unroll 1
     for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;
@@ -977,9 +1059,13 @@ __device__ __forceinline__ void tc_issuer_warp(TcShared* sh, int V, int n_pairs)
 #undef ISTEP
 }
 
+// SPLIT = false: the bf16-MLP path, two tiles per CTA.  SPLIT = true: the split-precision ("fp32") path, one tile per CTA, the
+// other tile group's warps idle (its operand slots hold the lo images).
 #if TC_TAB_PARAM
+template <bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant__ TcArgs A, const __grid_constant__ TcTables TAB) {
 #else
+template <bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
     unsigned char* smem = tc_smem_raw;
@@ -987,11 +1073,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = A.V;
     const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
-    const int n_pairs = (n_tiles + TC_TILES - 1) / TC_TILES;
+    constexpr int TPC = SPLIT ? 1 : TC_TILES;                  // tiles in flight per CTA
+    constexpr int AUXB = SPLIT ? TC_AUX_BYTES_SPLIT : TC_AUX_BYTES;
+    constexpr int NIMG = SPLIT ? 2 * TC_REC_IMAGES : TC_REC_IMAGES;    // operand images per (tile, view): hi [+ lo]
+    const int n_pairs = (n_tiles + TPC - 1) / TPC;
 #if TC_TAB_PARAM
-    tc_setup(smem, sh, nullptr, TC_TILES);
+    tc_setup(smem, sh, nullptr, TPC);
 #else
-    tc_setup(smem, sh, A.tab, TC_TILES);
+    tc_setup(smem, sh, A.tab, TPC);
 #endif
 
     // Register re-balancing (setmaxnreg, per warpgroup): 20 warps are launched at 96 registers so that the register
@@ -1000,12 +1089,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     if (warp >= TC_TILES * 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TC_REGS_PROD));
         // ===================================================== weight producer
-#if TC_ISSUER_SHARED
-        if (warp == TC_TILES * 8 + 1 || warp == TC_TILES * 8 + 2) tc_issuer_warp(warp - (TC_TILES * 8 + 1), sh, V, n_pairs);
-#else
-        if (warp == TC_TILES * 8 + 1) tc_issuer_warp<0>(sh, V, n_pairs);
-        else if (warp == TC_TILES * 8 + 2) tc_issuer_warp<1>(sh, V, n_pairs);
-#endif
+        if (warp == TC_TILES * 8 + 1 || (!SPLIT && warp == TC_TILES * 8 + 2)) tc_issuer_warp<SPLIT>(warp - (TC_TILES * 8 + 1), sh, V, n_pairs);
         else if (warp == TC_TILES * 8 && lane == 0) {
             uint32_t cc = 0;
 #pragma unroll 1
@@ -1020,8 +1104,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll 1
                     for (int rep = 0; rep < reps; ++rep)
 #pragma unroll 1
-                        for (int i = first; i < first + cnt; ++i)
+                        for (int i = first; i < first + cnt; ++i) {
                             tc_load_chunk(c_loads.src_off[i], c_loads.bytes[i], cc, smem, A.wblob, 300 + ph);
+                            if (SPLIT) tc_load_chunk(c_loads.src_off[i], c_loads.bytes[i], cc, smem, A.wblob + A.wblob_lo_off, 300 + ph);
+                        }
                 }
             }
         }
@@ -1037,25 +1123,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
         const int row = t.row, h = t.half, tg = t.tg;
         const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
 #pragma unroll 1
-        for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+        for (int pair = blockIdx.x; pair < (SPLIT && tg != 0 ? 0 : n_pairs); pair += gridDim.x) {
             // an odd tile count leaves the last pair's second group without a tile: it re-runs the last tile (the ring
             // needs both consumers) and stores nothing
-            const int tile_raw = pair * TC_TILES + tg;
+            const int tile_raw = pair * TPC + tg;
             const int tile = min(tile_raw, n_tiles - 1);
             const int isamp = tile_raw < n_tiles ? tile * TC_ROWS + row : A.n_chunk;
-            const unsigned char* aux_row = A.aux + ((size_t)tile * TC_ROWS + row) * V * TC_AUX_BYTES;
+            const unsigned char* aux_row = A.aux + ((size_t)tile * TC_ROWS + row) * V * AUXB;
             float wsum = 0.0f;
             // =========================================================== per-view geometry branch
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
-                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
+                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (NIMG * TC_SLOT);
                 if (leader) {          // all MMAs that read slots 0..3 have completed (last wait_acc)
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], 4 * TC_SLOT);
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 8 : 4) * TC_SLOT);
 #pragma unroll 1
-                    for (int s = 0; s < 4; ++s) tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                    for (int s = 0; s < 4; ++s) {
+                        tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                        if (SPLIT) tc::bulk_g2s(t.slot(s) + TC_LO_OFF, rimg + (TC_REC_IMAGES + s) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                    }
                 }
-                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                const float pw = reinterpret_cast<const float*>(aux_row + v * TC_AUX_BYTES)[7];
+                const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
+                const float pw = reinterpret_cast<const float*>(aux_row + v * AUXB)[7];
                 TC_PROF(5000 + v);
                 tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 400);
                 t.rec_phase ^= 1;
@@ -1087,9 +1176,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll
                     for (int s = 0; s < 3; ++s)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) t.gate_chunk1(s, 4 * h + c, g64[s]);
-                    if (h == 0) t.gate_chunk1(3, 2, g8[0]);
-                    else { t.gate_chunk1(3, 3, g8[1]); t.gate_chunk1(3, 4, g8[2]); }
+                        for (int c = 0; c < 4; ++c) t.template gate_chunk1<SPLIT>(s, 4 * h + c, g64[s]);
+                    if (h == 0) t.template gate_chunk1<SPLIT>(3, 2, g8[0]);
+                    else { t.template gate_chunk1<SPLIT>(3, 3, g8[1]); t.template gate_chunk1<SPLIT>(3, 4, g8[2]); }
                 }
                 // ---- G3: fused layer 1 (ReLU)
                 t.step(ST_G3);
@@ -1125,8 +1214,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
                         const float s2 = 2.0f * s1 * c1, c2 = 1.0f - 2.0f * s1 * s1;
                         const float s4 = 2.0f * s2 * c2, c4 = 1.0f - 2.0f * s2 * s2;
-                        t.st_chunk(pslot, 2 * j + h, make_uint4(tc_pack_scaled(dz, s1, w), tc_pack_scaled(c1, s2, w),
-                                                               tc_pack_scaled(c2, s4, w), tc::pack_bf16(c4 * w, 0.0f)));
+                        if constexpr (SPLIT) t.template put8<true>(pslot, 2 * j + h, dz * w, s1 * w, c1 * w, s2 * w, c2 * w, s4 * w, c4 * w, 0.0f);
+                        else t.st_chunk(pslot, 2 * j + h, make_uint4(tc_pack_scaled(dz, s1, w), tc_pack_scaled(c1, s2, w),
+                                                                    tc_pack_scaled(c2, s4, w), tc::pack_bf16(c4 * w, 0.0f)));
                     }
                     // P0..P4 commit to their ring-slot barrier, P5 completes the accumulator
                     t.issue(ST_P0 + s, s < 5 ? 1 + ps : 0);
@@ -1200,27 +1290,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { o[c0 + i] = m[i]; o[64 + c0 + i] = q[i]; }
                 }
-                t.st_chunk(1, (c0 >> 3), make_uint4(tc::pack_bf16(m[0], m[1]), tc::pack_bf16(m[2], m[3]), tc::pack_bf16(m[4], m[5]), tc::pack_bf16(m[6], m[7])));
-                t.st_chunk(1, (c0 >> 3) + 1, make_uint4(tc::pack_bf16(m[8], m[9]), tc::pack_bf16(m[10], m[11]), tc::pack_bf16(m[12], m[13]), tc::pack_bf16(m[14], m[15])));
-                t.st_chunk(2, (c0 >> 3), make_uint4(tc::pack_bf16(q[0], q[1]), tc::pack_bf16(q[2], q[3]), tc::pack_bf16(q[4], q[5]), tc::pack_bf16(q[6], q[7])));
-                t.st_chunk(2, (c0 >> 3) + 1, make_uint4(tc::pack_bf16(q[8], q[9]), tc::pack_bf16(q[10], q[11]), tc::pack_bf16(q[12], q[13]), tc::pack_bf16(q[14], q[15])));
+                t.template put8<SPLIT>(1, (c0 >> 3), m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+                t.template put8<SPLIT>(1, (c0 >> 3) + 1, m[8], m[9], m[10], m[11], m[12], m[13], m[14], m[15]);
+                t.template put8<SPLIT>(2, (c0 >> 3), q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
+                t.template put8<SPLIT>(2, (c0 >> 3) + 1, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
             }
             t.step(ST_Q1);
             uint4 lat_a = make_uint4(0, 0, 0, 0), lat_b = make_uint4(0, 0, 0, 0);      // h=0: latent cols 0-15, h=1: cols 16-23
+            uint4 lat_al = make_uint4(0, 0, 0, 0), lat_bl = make_uint4(0, 0, 0, 0);    // their lo parts (split path)
+            auto split8 = [](const float* x, uint4& hi, uint4& lo) {
+                const float f[8] = {x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]};
+                hi = pack8(f);
+                float fh[8], fl[8];
+                unpack8(hi, fh);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) fl[i] = f[i] - fh[i];
+                lo = pack8(fl);
+            };
             EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST0) + 32 * h, 4, 4 * h);
             if (h == 0) {
                 float x[16];
                 t.ld16(64, x);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) x[i] += BIASP(L_COMPRESS)[i];
-                lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
-                lat_b = make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15]));
+                split8(x, lat_a, lat_al);
+                split8(x + 8, lat_b, lat_bl);
             } else {
                 float x[8];
                 t.ld8(80, x);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] += BIASP(L_COMPRESS)[16 + i];
-                lat_a = make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7]));
+                split8(x, lat_a, lat_al);
             }
             t.step(ST_Q2);
             EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST1) + 32 * h, 0, 4 * h);
@@ -1235,22 +1335,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             // =========================================================== texture branch per view
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
-                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (TC_REC_IMAGES * TC_SLOT);
+                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (NIMG * TC_SLOT);
                 if (leader) {
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], TC_SLOT);
+                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 2 : 1) * TC_SLOT);
                     tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                    if (SPLIT) tc::bulk_g2s(t.slot(1) + TC_LO_OFF, rimg + (TC_REC_IMAGES + 4) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
                 }
                 // tail operand [lat24 | extras 8] in slot 2, ray difference (4) in slot 3 cols 0..15
                 if (h == 0) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                    const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
+                    const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
+                    const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 16);
                     t.st_chunk(2, 0, lat_a);
                     t.st_chunk(2, 1, lat_b);
-                    t.st_chunk(3, 0, make_uint4(tc::pack_bf16(a0.w, a1.x), tc::pack_bf16(a1.y, a1.z), 0, 0));
-                    t.st_chunk(3, 1, make_uint4(0, 0, 0, 0));
+                    if (SPLIT) { t.st_chunk_lo(2, 0, lat_al); t.st_chunk_lo(2, 1, lat_bl); }
+                    t.template put8<SPLIT>(3, 0, a0.w, a1.x, a1.y, a1.z, 0.0f, 0.0f, 0.0f, 0.0f);
+                    t.template zero8<SPLIT>(3, 1);
                 } else {
                     t.st_chunk(2, 2, lat_a);
-                    t.st_chunk(2, 3, *reinterpret_cast<const uint4*>(aux_row + v * TC_AUX_BYTES + 48));
+                    if constexpr (SPLIT) {        // the 8 extras [a g, a b, b r, b g, b b, qvis, vn, vt] travel as fp32 in the split side record
+                        t.st_chunk_lo(2, 2, lat_al);
+                        const float4 e0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 48);
+                        const float4 e1 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 64);
+                        t.template put8<true>(2, 3, e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w);
+                    } else {
+                        t.st_chunk(2, 3, *reinterpret_cast<const uint4*>(aux_row + v * AUXB + 48));
+                    }
                 }
                 TC_PROF(5200 + v);
                 tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 401);
@@ -1275,15 +1384,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     // slot 1 chunks: 0 -> g0, 1 -> g1, 2 -> g2, 3,4 -> g3, 5,6 -> g4, 7 -> [g3,g3,g4,g4,g0,g0,g0,g1]
                     // slot 2 chunks: 0..2 -> g5, 3 -> [g1,g1,g2,g2,g2,1,1,1]      (kTexMap1 / kTexMap2)
                     if (h == 0) {
-                        t.gate_chunk1(1, 0, gt[0]); t.gate_chunk1(1, 1, gt[1]); t.gate_chunk1(1, 2, gt[2]); t.gate_chunk1(1, 3, gt[3]);
-                        t.gate_chunk1(2, 0, gt[5]); t.gate_chunk1(2, 1, gt[5]);
+                        t.template gate_chunk1<SPLIT>(1, 0, gt[0]); t.template gate_chunk1<SPLIT>(1, 1, gt[1]); t.template gate_chunk1<SPLIT>(1, 2, gt[2]); t.template gate_chunk1<SPLIT>(1, 3, gt[3]);
+                        t.template gate_chunk1<SPLIT>(2, 0, gt[5]); t.template gate_chunk1<SPLIT>(2, 1, gt[5]);
                     } else {
-                        t.gate_chunk1(1, 4, gt[3]); t.gate_chunk1(1, 5, gt[4]); t.gate_chunk1(1, 6, gt[4]);
+                        t.template gate_chunk1<SPLIT>(1, 4, gt[3]); t.template gate_chunk1<SPLIT>(1, 5, gt[4]); t.template gate_chunk1<SPLIT>(1, 6, gt[4]);
                         const float g7[8] = {gt[3], gt[3], gt[4], gt[4], gt[0], gt[0], gt[0], gt[1]};
-                        t.gate_chunk(1, 7, g7);
-                        t.gate_chunk1(2, 2, gt[5]);
+                        t.template gate_chunk<SPLIT>(1, 7, g7);
+                        t.template gate_chunk1<SPLIT>(2, 2, gt[5]);
                         const float g3[8] = {gt[1], gt[1], gt[2], gt[2], gt[2], 1.0f, 1.0f, 1.0f};
-                        t.gate_chunk(2, 3, g3);
+                        t.template gate_chunk<SPLIT>(2, 3, g3);
                     }
                     const int fcol = TC_SREG + 40 * v;
                     if (h == 0) {
@@ -1349,8 +1458,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 for (int v = 0; v < TC_MAXV; ++v) {
                     e[v] = 0.f; wt[v] = 0.f; sv[v] = -1e4f;
                     if (v < V) {
-                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
-                        const float4 a2 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 32);
+                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 16);
+                        const float4 a2 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 32);
                         maskv = a2.x;
                         e[v] = __expf(t.tb->ani_al_abs * (a1.z - 1.0f));
                         emin = fminf(emin, e[v]);
@@ -1399,26 +1508,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         for (int v = 0; v < TC_MAXV; ++v) { const float d = f[v][i] - mu; va += wt[v] * d * d; }
                         mean[i] = mu; var[i] = va;
                     }
-                    t.st_chunk(1, g, pack8(mean));                               // mean -> slot 1 cols 0..39
-                    if (g < 3) t.st_chunk(1, 5 + g, pack8(var));                 // var 0..23 -> slot 1 cols 40..63
+                    t.template put8<SPLIT>(1, g, mean);                               // mean -> slot 1 cols 0..39
+                    if (g < 3) t.template put8<SPLIT>(1, 5 + g, var);                 // var 0..23 -> slot 1 cols 40..63
 #pragma unroll
                     for (int v = 0; v < TC_MAXV; ++v) {
                         if (v < V) {
-                            if (g >= 3) t.st_chunk(2 + v, g - 3, pack8(var));    // var 24..39 -> slot 2+v cols 0..15
-                            t.st_chunk(2 + v, 2 + g, pack8(f[v]));               // f_v -> slot 2+v cols 16..55
+                            if (g >= 3) t.template put8<SPLIT>(2 + v, g - 3, var);    // var 24..39 -> slot 2+v cols 0..15
+                            t.template put8<SPLIT>(2 + v, 2 + g, f[v]);               // f_v -> slot 2+v cols 16..55
                         }
                     }
                 }
                 if (h == 1) {
 #pragma unroll
-                    for (int v = 0; v < TC_MAXV; ++v) if (v < V) t.st_chunk(2 + v, 7, make_uint4(0, 0, 0, 0));
+                    for (int v = 0; v < TC_MAXV; ++v) if (v < V) t.template zero8<SPLIT>(2 + v, 7);
                 }
             }
             // all reads of the f columns precede the accumulator writes of I1 (ordered by the step's publish)
             t.step(ST_I1);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
-                if (v < V) tc_epi_store<TA_ELU, 2>(t, 64 * v + 32 * h, BIASP(L_BASE0) + 32 * h, t.slot(2 + v), 4 * h);
+                if (v < V) tc_epi_store<TA_ELU, 2, SPLIT>(t, 64 * v + 32 * h, BIASP(L_BASE0) + 32 * h, t.slot(2 + v), 4 * h);
             t.step(ST_I2);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
@@ -1432,15 +1541,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         y[i] = x[i] * wv;
                     }
                     t.st16(160 + 32 * v + 16 * h, x);
-                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
-                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                    t.template put8<SPLIT>(2 + v, 2 * h, y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+                    t.template put8<SPLIT>(2 + v, 2 * h + 1, y[8], y[9], y[10], y[11], y[12], y[13], y[14], y[15]);
                 }
             }
             tc::tmem_st_wait();
             t.step(ST_I3);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
-                if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS1_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
+                if (v < V) tc_epi_store<TA_ELU, 1, SPLIT>(t, 48 * v + 16 * h, BIASP(L_VIS1_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I4);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
@@ -1456,15 +1565,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         y[i] = x[i] * vis;
                     }
                     t.st16(160 + 32 * v + 16 * h, x);
-                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(y[0], y[1]), tc::pack_bf16(y[2], y[3]), tc::pack_bf16(y[4], y[5]), tc::pack_bf16(y[6], y[7])));
-                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(y[8], y[9]), tc::pack_bf16(y[10], y[11]), tc::pack_bf16(y[12], y[13]), tc::pack_bf16(y[14], y[15])));
+                    t.template put8<SPLIT>(2 + v, 2 * h, y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+                    t.template put8<SPLIT>(2 + v, 2 * h + 1, y[8], y[9], y[10], y[11], y[12], y[13], y[14], y[15]);
                 }
             }
             tc::tmem_st_wait();
             t.step(ST_I5);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
-                if (v < V) tc_epi_store<TA_ELU, 1>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
+                if (v < V) tc_epi_store<TA_ELU, 1, SPLIT>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I6);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
@@ -1474,25 +1583,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     t.ld16(160 + 32 * v + 16 * h, x);
                     const float vis2 = tc_act<TA_SIGMOID>(vv[0] + BIASP(L_VIS2_1)[0]) * maskv;
                     // out_layer input [x 32 | vis | ray_diff 4] -> slot 2+v cols 0..47
-                    t.st_chunk(2 + v, 2 * h, make_uint4(tc::pack_bf16(x[0], x[1]), tc::pack_bf16(x[2], x[3]), tc::pack_bf16(x[4], x[5]), tc::pack_bf16(x[6], x[7])));
-                    t.st_chunk(2 + v, 2 * h + 1, make_uint4(tc::pack_bf16(x[8], x[9]), tc::pack_bf16(x[10], x[11]), tc::pack_bf16(x[12], x[13]), tc::pack_bf16(x[14], x[15])));
+                    t.template put8<SPLIT>(2 + v, 2 * h, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+                    t.template put8<SPLIT>(2 + v, 2 * h + 1, x[8], x[9], x[10], x[11], x[12], x[13], x[14], x[15]);
                     if (h == 0) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES);
-                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * TC_AUX_BYTES + 16);
-                        t.st_chunk(2 + v, 4, make_uint4(tc::pack_bf16(vis2, a0.w), tc::pack_bf16(a1.x, a1.y), tc::pack_bf16(a1.z, 0.f), 0));
+                        const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
+                        const float4 a1 = *reinterpret_cast<const float4*>(aux_row + v * AUXB + 16);
+                        t.template put8<SPLIT>(2 + v, 4, vis2, a0.w, a1.x, a1.y, a1.z, 0.0f, 0.0f, 0.0f);
                     } else {
-                        t.st_chunk(2 + v, 5, make_uint4(0, 0, 0, 0));
+                        t.template zero8<SPLIT>(2 + v, 5);
                     }
                 }
             }
             t.step(ST_I7);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
-                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
+                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
             t.step(ST_I8);
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
-                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
+                if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
             t.step(ST_I9);
             if (h == 0) {
                 TC_VLOOP

@@ -50,6 +50,9 @@ struct vanerf_ctx {
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
     int tc_waves = 16;
+    int split_waves = 8;               // tiles per CTA and launch of the split-precision path
+    unsigned tcw_lo_off = 0;           // byte offset of the lo weight images inside tcw
+    bool fp32_simt = false;            // VANERF_FP32_SIMT=1: fp32 path on the FFMA kernel (k_mlp_simt) instead of the split-precision tensor-core kernel
     DevBuf tcw, tctab, geo0b, geo1b, texb, T64b, T8b, Ttexb, tc_rec, tc_aux, gf_scratch;
     FrameTc ft;
     int* tc_err_host = nullptr;        // mapped pinned int written by the kernels (bounded waits that gave up)
@@ -156,12 +159,14 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
     memset(&c->ft, 0, sizeof(c->ft));
     memset(&c->h_tc, 0, sizeof(c->h_tc));
     memset(&c->h_prog, 0, sizeof(c->h_prog));
-    if (cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_tc_mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * TC_SLOT + 1024) != cudaSuccess) {
         cudaFreeHost(c->tc_err_host); delete c; return VANERF_ERR_CUDA;
     }
     if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));      // developer override
+    if (const char* w = getenv("VANERF_FP32_SIMT")) c->fp32_simt = atoi(w) != 0;                            // developer override
     if (const char* w = getenv("VANERF_REUSE_GEOM")) c->reuse_geometry = atoi(w) != 0;                      // developer override
 #endif
     *out = c;
@@ -252,14 +257,17 @@ int vanerf_load_weights(vanerf_ctx* ctx, const vanerf_weights* w, void* stream) 
     CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));   // host staging buffers go out of scope
 #ifndef VANERF_HOST_EMUL
     {   // tensor-core path: step tables + swizzled bf16 weight images
-        std::vector<uint16_t> img;
+        std::vector<uint16_t> img, img_lo;
         float kpt_keep[TC_MAXV * NKPT * 4];
         memcpy(kpt_keep, ctx->h_tc.kpt4, sizeof(kpt_keep));
-        tc_build(src, w->ani_al, ctx->h_tc, ctx->h_prog, img);
+        tc_build(src, w->ani_al, ctx->h_tc, ctx->h_prog, img, &img_lo);
         memcpy(ctx->h_tc.kpt4, kpt_keep, sizeof(kpt_keep));
         ctx->tc_tab_dirty = true;
-        ENSURE(ctx, ctx->tcw, img.size() * 2);
+        // bf16 weight images [hi | lo]: the bf16 path streams the hi half, the split-precision path both
+        ctx->tcw_lo_off = (unsigned)(img.size() * 2);
+        ENSURE(ctx, ctx->tcw, img.size() * 4);
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tcw.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync((unsigned char*)ctx->tcw.p + img.size() * 2, img_lo.data(), img_lo.size() * 2, cudaMemcpyHostToDevice, (cudaStream_t)stream));
         CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     }
 #endif
@@ -524,15 +532,59 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
         TcArgs a;
         a.tab = (const TcTables*)ctx->tctab.p; a.wblob = (const unsigned char*)ctx->tcw.p;
         a.rec = (const unsigned char*)ctx->tc_rec.p; a.aux = (const unsigned char*)ctx->tc_aux.p;
-        a.V = V; a.n_chunk = nc; a.sample0 = s0;
+        a.V = V; a.n_chunk = nc; a.sample0 = s0; a.wblob_lo_off = ctx->tcw_lo_off;
         a.rgba = rgba; a.raw_out = raw_out; a.dbg_latent = dbg_latent; a.err = ctx->tc_err_dev;
 #if TC_TAB_PARAM
         // the tables (biases, small fp32 layers, camera-space keypoints of the frame) travel by value in the kernel
         // parameter: constant-bank reads with warp-uniform addresses, no shared memory, no context-global state
-        VANERF_LAUNCH(k_mlp_tc, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
+        VANERF_LAUNCH(k_mlp_tc<false>, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
 #else
-        VANERF_LAUNCH(k_mlp_tc, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a);
+        VANERF_LAUNCH(k_mlp_tc<false>, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a);
 #endif
+        CHECK_LAUNCH(ctx);
+    }
+    return VANERF_OK;
+}
+#endif
+
+#if !defined(VANERF_HOST_EMUL) && TC_TAB_PARAM
+// Split-precision ("fp32") tensor-core shading: fp32 gather records (k_gather) -> bf16 hi / lo operand images (k_rec_split) ->
+// k_mlp_tc<true> (three MMAs per K step, one tile per CTA), in chunks of sm_count x split_waves tiles.
+static int tc_shade_split(vanerf_ctx* ctx, const TargetDev& td, const float* rays, const float* z, int S, long long N, const float* sdf,
+                          const int* nn, const unsigned char* qvis, float* rgba, unsigned char* valid, float* raw_out, float* dbg_latent,
+                          cudaStream_t stream, const float* pts_in, const float* view_in) {
+    const int V = ctx->fr.V;
+    if (tc_take_error(ctx)) return VANERF_ERR_CUDA;
+    if (!tc_program_matches(ctx->h_prog)) {
+        snprintf(ctx->err, sizeof(ctx->err), "tensor-core path: packing script and compiled MMA program disagree");
+        return VANERF_ERR_STATE;
+    }
+    const int max_tiles = ctx->sm_count * ctx->split_waves;
+    const long long chunk = (long long)max_tiles * TC_ROWS;
+    ENSURE(ctx, ctx->rec, (size_t)chunk * V * REC_STRIDE * 4);
+    ENSURE(ctx, ctx->tc_rec, (size_t)max_tiles * V * 2 * TC_REC_IMAGES * TC_SLOT);
+    ENSURE(ctx, ctx->tc_aux, (size_t)max_tiles * TC_ROWS * V * TC_AUX_BYTES_SPLIT);
+    for (long long s0 = 0; s0 < N; s0 += chunk) {
+        const int nc = (int)((N - s0) < chunk ? (N - s0) : chunk);
+        const int n_tiles = cdiv(nc, TC_ROWS);
+        {
+            TimedScope ts(ctx, KCL_GATHER, stream);
+            const int gblocks = min(cdiv(nc, GATHER_THREADS / 16), ctx->sm_count * 8);
+            VANERF_LAUNCH(k_gather, gblocks, GATHER_THREADS, 0, stream, ctx->fr, td, rays, z, pts_in, view_in, S, s0, nc, N, sdf, nn, qvis,
+                          (float*)ctx->rec.p, valid);
+            CHECK_LAUNCH(ctx);
+            const long long n_thr = (long long)n_tiles * TC_ROWS * V * (TC_REC_IMAGES * 8 + 6);
+            VANERF_LAUNCH(k_rec_split, cdiv(n_thr, 256), 256, 0, stream, (const float*)ctx->rec.p, V, nc, (unsigned char*)ctx->tc_rec.p,
+                          (unsigned char*)ctx->tc_aux.p);
+            CHECK_LAUNCH(ctx);
+        }
+        TimedScope ts(ctx, KCL_MLP, stream);
+        TcArgs a;
+        a.tab = nullptr; a.wblob = (const unsigned char*)ctx->tcw.p; a.wblob_lo_off = ctx->tcw_lo_off;
+        a.rec = (const unsigned char*)ctx->tc_rec.p; a.aux = (const unsigned char*)ctx->tc_aux.p;
+        a.V = V; a.n_chunk = nc; a.sample0 = s0;
+        a.rgba = rgba; a.raw_out = raw_out; a.dbg_latent = dbg_latent; a.err = ctx->tc_err_dev;
+        VANERF_LAUNCH(k_mlp_tc<true>, min(n_tiles, ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
         CHECK_LAUNCH(ctx);
     }
     return VANERF_OK;
@@ -551,6 +603,12 @@ static int shade_impl(vanerf_ctx* ctx, int precision, const TargetDev& td, const
 #ifndef VANERF_HOST_EMUL
     if (precision == VANERF_BF16)
         return tc_shade(ctx, td, rays, z, S, N, sdf, nn, qvis, rgba, valid, raw_out, dbg_latent, stream, pts_in, view_in);
+#if TC_TAB_PARAM
+    // fp32 path: split-precision tensor-core kernel (up to 3 source views); the FFMA kernel below serves V = 4 and the
+    // VANERF_FP32_SIMT=1 developer switch
+    if (!ctx->fp32_simt && V <= TC_MAXV)
+        return tc_shade_split(ctx, td, rays, z, S, N, sdf, nn, qvis, rgba, valid, raw_out, dbg_latent, stream, pts_in, view_in);
+#endif
 #endif
     const int chunk = (int)(N < SHADE_CHUNK ? N : SHADE_CHUNK);
     ENSURE(ctx, ctx->rec, (size_t)chunk * V * REC_STRIDE * 4);
