@@ -577,6 +577,27 @@ def main():
         dres = measure_dynamic(args, net, args.frames, 1, 1)
         if rank == 0:
             line["workload_D"] = dres
+        if world == 1:
+            # the step in front of the path: source images -> feature maps, cuDNN through vanerf_b200/encoders.py
+            enc = net.build_encoders(seed=1)
+            ims = torch.rand(V, 3, H, W, device=dev)
+            blk = {}
+            for tag, dt in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+                enc.autocast_dtype = dt
+                for _ in range(2):
+                    enc.encode_geo(ims); enc.encode_tex(ims)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    g = enc.encode_geo(ims); t = enc.encode_tex(ims)
+                e1.record()
+                torch.cuda.synchronize()
+                blk["ms_per_frame_" + tag] = e0.elapsed_time(e1) / 3
+            blk["maps"] = {"geo0": list(g[0].shape), "geo1": list(g[1].shape), "tex": list(t.shape)}
+            blk["note"] = "HGFilterV2 + ResBlkEncoder (28.3 M parameters) on V=3 source images of 334x512, channels_last, cuDNN: library code, outside the hot path"
+            line["encoders"] = blk
+            net.encoders = None
         del net, r
         torch.cuda.empty_cache()
         eres = measure_train(args, 2, 1)

@@ -93,9 +93,23 @@
 #ifndef TC_PREWAIT
 #define TC_PREWAIT 1                     // issuer waits for a step's weight chunks before it waits for the step's operands: -9 %
 #endif
+#ifndef TC_STAGGER
+#define TC_STAGGER 0                     // cycles between the start phases of CTA groups (blockIdx % TC_STAGGER_GROUPS)
+#endif
+#ifndef TC_STAGGER_GROUPS
+#define TC_STAGGER_GROUPS 16
+#endif
+#ifndef TC_REC_EARLY
+#define TC_REC_EARLY 0                   // bit mask: operand images requested one step before they are needed (see load_geo / load_tex):
+                                         // 1 next view's geometry images after M3, 2 first texture image after Q1, 4 next texture image after T3, 8 next tile's images after I9
+#endif
+#ifndef TC_PE_UNROLL
+#define TC_PE_UNROLL 0                   // the four keypoints of a PE step as independent instruction streams (the rolled loop is one dependent chain per keypoint)
+#endif
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
-#endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating
+#endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating,
+                                         // 32 no proxy fence, 64 no waits for weight chunks, 128 no operand-image loads
 enum TcStepId {
     ST_G1 = 0, ST_G2, ST_G3, ST_G4, ST_M0, ST_P0, ST_P1, ST_P2, ST_P3, ST_P4, ST_P5, ST_M1, ST_M2, ST_M3,
     ST_Q1, ST_Q2, ST_Q3, ST_T1, ST_T2, ST_T3, ST_T4, ST_I1, ST_I2, ST_I3, ST_I4, ST_I5, ST_I6, ST_I7, ST_I8, ST_I9,
@@ -666,7 +680,9 @@ __device__ __forceinline__ void tc_prewait_chunks(uint32_t cc, TcShared* sh) {
     constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
     if (first_in_chunk) {
         const uint32_t c = cc + op.chunk_rel;
+#if !(TC_ABLATE & 64)
         tc::mbar_wait(&sh->wfull[c % TC_NRING], (c / TC_NRING) & 1, sh->abort_flag, 100 + ST);
+#endif
     }
     if constexpr (I + 1 < S.nops) tc_prewait_chunks<ST, I + 1>(cc, sh);
 }
@@ -820,7 +836,9 @@ struct TcTile {
     __device__ __forceinline__ void issue(int st, int commit_to) {
         (void)st; (void)commit_to;            // the issuer warp walks the same static sequence (TcProg::seq_*)
         TC_PROF(1000 + st);                   // epilogue of the previous step done (this thread)
+#if !(TC_ABLATE & 32)
         tc::fence_proxy_async();
+#endif
         TC_PROF(2000 + st);                   // proxy fence done
         tc::tcgen05_fence_before();
         __syncwarp();
@@ -1122,6 +1140,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
         const int row = t.row, h = t.half, tg = t.tg;
         const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
+#if TC_STAGGER
+        // CTAs start out of phase: all of them run the same program on the same amount of work, so without this they request
+        // their operand images from HBM in the same few hundred cycles, every time (148 x 64 KB bursts at the full HBM rate).
+        if (gridDim.x > TC_STAGGER_GROUPS) {
+            const long long t_go = clock64() + (long long)(blockIdx.x % TC_STAGGER_GROUPS) * TC_STAGGER;
+            while (clock64() < t_go) __nanosleep(200);
+        }
+#endif
+        bool prefetched = false;                                 // leader: the next tile's first images are already on their way
 #pragma unroll 1
         for (int pair = blockIdx.x; pair < (SPLIT && tg != 0 ? 0 : n_pairs); pair += gridDim.x) {
             // an odd tile count leaves the last pair's second group without a tile: it re-runs the last tile (the ring
@@ -1131,22 +1158,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             const int isamp = tile_raw < n_tiles ? tile * TC_ROWS + row : A.n_chunk;
             const unsigned char* aux_row = A.aux + ((size_t)tile * TC_ROWS + row) * V * AUXB;
             float wsum = 0.0f;
+            // Operand images of (tile, view) -> slots 0..3 / texture image -> slot 1, requested by the group's leader as soon as
+            // the last MMA that reads the target slots has completed (TC_REC_EARLY: one step before they are needed, so that the
+            // HBM latency of the images hides behind the pooling sums / the steps in between; 0 = at the point of use).
+            auto load_geo = [&](int tl, int v) {
+                if (TC_ABLATE & 128) return;
+                const unsigned char* rimg = A.rec + ((size_t)tl * V + v) * (NIMG * TC_SLOT);
+                tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 8 : 4) * TC_SLOT);
+#pragma unroll 1
+                for (int s = 0; s < 4; ++s) {
+                    tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                    if (SPLIT) tc::bulk_g2s(t.slot(s) + TC_LO_OFF, rimg + (TC_REC_IMAGES + s) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                }
+            };
+            auto load_tex = [&](int v) {
+                if (TC_ABLATE & 128) return;
+                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (NIMG * TC_SLOT);
+                tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 2 : 1) * TC_SLOT);
+                tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+                if (SPLIT) tc::bulk_g2s(t.slot(1) + TC_LO_OFF, rimg + (TC_REC_IMAGES + 4) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
+            };
             // =========================================================== per-view geometry branch
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
-                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (NIMG * TC_SLOT);
-                if (leader) {          // all MMAs that read slots 0..3 have completed (last wait_acc)
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 8 : 4) * TC_SLOT);
-#pragma unroll 1
-                    for (int s = 0; s < 4; ++s) {
-                        tc::bulk_g2s(t.slot(s), rimg + s * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
-                        if (SPLIT) tc::bulk_g2s(t.slot(s) + TC_LO_OFF, rimg + (TC_REC_IMAGES + s) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
-                    }
+                // all MMAs that read slots 0..3 have completed (last wait_acc)
+                if (leader) {
+                    if (v == 0 ? !prefetched : !(TC_REC_EARLY & 1)) load_geo(tile, v);
+                    prefetched = false;
                 }
                 const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
                 const float pw = reinterpret_cast<const float*>(aux_row + v * AUXB)[7];
                 TC_PROF(5000 + v);
-                tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 400);
+                if (!(TC_ABLATE & 128)) tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 400);
                 t.rec_phase ^= 1;
                 TC_PROF(5100 + v);
                 // ---- G1: attention layer 1 of both scales -> acc cols 0..15 (scale 64), 16..31 (scale 8)
@@ -1199,8 +1242,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         t.pfree_bits ^= 1u << ps;
                     }
                     const int nk = s < 5 ? 4 : 1;
+#if TC_PE_UNROLL
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j >= nk) break;
+#else
 #pragma unroll 1
                     for (int j = 0; j < nk; ++j) {
+#endif
                         const int kp = 8 * s + 2 * j + h;
                         const float4 kc = reinterpret_cast<const float4*>(t.tb->kpt4)[v * NKPT + kp];
                         const float dx = a0.x - kc.x, dy = a0.y - kc.y, dz = a0.z - kc.z;
@@ -1243,6 +1292,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
                 t.step(ST_M3);
 #endif
+                if ((TC_REC_EARLY & 1) && leader && v + 1 < V) load_geo(tile, v + 1);      // M3 (the last reader of slots 1, 2) has completed
                 // ---- weighted pooling sums over views in TMEM: S1 += w h3, S2 += w h3^2 (pool_ops, src/utils.py:854-880)
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
@@ -1296,6 +1346,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 t.template put8<SPLIT>(2, (c0 >> 3) + 1, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
             }
             t.step(ST_Q1);
+            if ((TC_REC_EARLY & 2) && leader) load_tex(0);             // Q1 was the last reader of slot 1
             uint4 lat_a = make_uint4(0, 0, 0, 0), lat_b = make_uint4(0, 0, 0, 0);      // h=0: latent cols 0-15, h=1: cols 16-23
             uint4 lat_al = make_uint4(0, 0, 0, 0), lat_bl = make_uint4(0, 0, 0, 0);    // their lo parts (split path)
             auto split8 = [](const float* x, uint4& hi, uint4& lo) {
@@ -1335,12 +1386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             // =========================================================== texture branch per view
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
-                const unsigned char* rimg = A.rec + ((size_t)tile * V + v) * (NIMG * TC_SLOT);
-                if (leader) {
-                    tc::mbar_arrive_expect_tx(&sh->rec_bar[tg], (SPLIT ? 2 : 1) * TC_SLOT);
-                    tc::bulk_g2s(t.slot(1), rimg + 4 * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
-                    if (SPLIT) tc::bulk_g2s(t.slot(1) + TC_LO_OFF, rimg + (TC_REC_IMAGES + 4) * TC_SLOT, TC_SLOT, &sh->rec_bar[tg]);
-                }
+                if (leader && (v == 0 ? !(TC_REC_EARLY & 2) : !(TC_REC_EARLY & 4))) load_tex(v);
                 // tail operand [lat24 | extras 8] in slot 2, ray difference (4) in slot 3 cols 0..15
                 if (h == 0) {
                     const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
@@ -1362,7 +1408,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     }
                 }
                 TC_PROF(5200 + v);
-                tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 401);
+                if (!(TC_ABLATE & 128)) tc_wait(&sh->rec_bar[tg], t.rec_phase, sh->abort_flag, 401);
                 t.rec_phase ^= 1;
                 TC_PROF(5300 + v);
                 // ---- T1: attention layer 1 (ReLU) + ray encoder layer 1 (ELU)
@@ -1416,6 +1462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 }
                 // ---- T3: fused layer 1 (ReLU)
                 t.step(ST_T3);
+                if ((TC_REC_EARLY & 4) && leader && v + 1 < V) load_tex(v + 1);           // T3 was the last reader of slot 1
                 if (h == 0) EPI(TA_RELU, 0, 3, NOBIAS, 4, 0);
                 else {
                     EPI(TA_RELU, 48, 1, NOBIAS, 4, 6);
@@ -1603,6 +1650,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
             t.step(ST_I9);
+            if ((TC_REC_EARLY & 8) && leader) {                 // every MMA of this tile has completed: the next tile's first images
+                const int pair_n = pair + gridDim.x;
+                prefetched = pair_n < n_pairs;
+                if (prefetched) load_geo(min(pair_n * TPC + tg, n_tiles - 1), 0);
+            }
             if (h == 0) {
                 TC_VLOOP
                 for (int v = 0; v < TC_MAXV; ++v) {
@@ -1651,6 +1703,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             if (leader) sh->stop[tg] = *reinterpret_cast<volatile int*>(sh->abort_flag);
             tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
             if (*reinterpret_cast<volatile int*>(&sh->stop[tg])) break;
+        }
+        if (TC_REC_EARLY && leader && prefetched) {              // left the loop on an abort with images in flight: they must land before the CTA exits
+#pragma unroll 1
+            for (int it = 0; it < TC_WAIT_TRIES && !tc::mbar_try_wait(&sh->rec_bar[tg], t.rec_phase); ++it) {}
         }
     }
     tc_teardown(sh, A.err);

@@ -50,6 +50,7 @@ struct vanerf_ctx {
     TcProg h_prog;                     // static MMA program (layer shapes only); uploaded to __constant__ c_prog
     bool tc_tab_dirty = true;
     int tc_waves = 16;
+    int tc_grid = 1 << 30;            // developer override (VANERF_TC_GRID): cap on the CTAs of k_mlp_tc<false> (scaling experiments)
     int split_waves = 8;               // tiles per CTA and launch of the split-precision path
     unsigned tcw_lo_off = 0;           // byte offset of the lo weight images inside tcw
     bool fp32_simt = false;            // VANERF_FP32_SIMT=1: fp32 path on the FFMA kernel (k_mlp_simt) instead of the split-precision tensor-core kernel
@@ -166,6 +167,7 @@ int vanerf_ctx_create(vanerf_ctx** out, int device) {
         cudaFreeHost(c->tc_err_host); delete c; return VANERF_ERR_CUDA;
     }
     if (const char* w = getenv("VANERF_TC_WAVES")) c->tc_waves = std::max(1, std::min(16, atoi(w)));      // developer override
+    if (const char* w = getenv("VANERF_TC_GRID")) c->tc_grid = std::max(1, atoi(w));                         // developer override
     if (const char* w = getenv("VANERF_FP32_SIMT")) c->fp32_simt = atoi(w) != 0;                            // developer override
     if (const char* w = getenv("VANERF_REUSE_GEOM")) c->reuse_geometry = atoi(w) != 0;                      // developer override
 #endif
@@ -537,7 +539,7 @@ static int tc_shade(vanerf_ctx* ctx, const TargetDev& td, const float* rays, con
 #if TC_TAB_PARAM
         // the tables (biases, small fp32 layers, camera-space keypoints of the frame) travel by value in the kernel
         // parameter: constant-bank reads with warp-uniform addresses, no shared memory, no context-global state
-        VANERF_LAUNCH(k_mlp_tc<false>, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
+        VANERF_LAUNCH(k_mlp_tc<false>, min(min(cdiv(n_tiles, TC_TILES), ctx->sm_count), ctx->tc_grid), TC_THREADS, TC_SMEM_BYTES, stream, a, ctx->h_tc);
 #else
         VANERF_LAUNCH(k_mlp_tc<false>, min(cdiv(n_tiles, TC_TILES), ctx->sm_count), TC_THREADS, TC_SMEM_BYTES, stream, a);
 #endif

@@ -4,8 +4,9 @@
 `render_pifu_nerf`, `batch_render_pifu_nerf`, `query`, `rgba2out`, `importance_sample`, `ray_bbox_intersection`,
 `sdf_activation`, `attach_*_feat` — so `VANeRFLightningModule.render_full_nerf_image` / `render_novel_views`
 (src/model.py:488-545) can run on top of it unmodified.  Everything per ray / per sample is executed by
-libvanerf_b200.so through `Renderer`; the CNN encoders are outside the path: their feature maps are
-passed in (`feat_geo`, `feat_tex`) or attached with `attach_im_feat(feat_geo=..., feat_tex=...)`.
+libvanerf_b200.so through `Renderer`; the CNN encoders are the step in front of the path (cuDNN through
+vanerf_b200/encoders.py): their feature maps are passed in (`feat_geo`, `feat_tex`), attached with `attach_im_feat(feat_geo=...,
+feat_tex=...)`, or computed from the source images once `build_encoders()` / a checkpoint with encoder weights has provided them.
 
 Supported configuration: batch size 1 (like every reference config), 1..4 source views (3 on the bf16 path;
 V-generalisation of SURVEY.md Appendix C), any H x W.  Inference (`uniform=True`, eval mode) runs the fused kernels.  The
@@ -36,6 +37,7 @@ class VANeRF:
         self.training = False
         self.feat_geo = None
         self.feat_tex = None
+        self.encoders = None                  # vanerf_b200.encoders.Encoders (build_encoders / checkpoint with encoder weights)
         self._frame_key = None
         self._frame_refs = None
         self._state_dict = None
@@ -71,26 +73,54 @@ class VANeRF:
     def load_state_dict(self, state_dict, strict=False):
         self.renderer.load_state_dict(state_dict)
         self._state_dict = dict(state_dict)
+        enc = {k: v for k, v in state_dict.items() if k.startswith(("geo_encoder.", "tex_encoder."))}
+        if enc:                               # a full reference checkpoint: the encoders come with it
+            self.build_encoders()
+            self.encoders.load_state_dict({k: torch.as_tensor(v) for k, v in enc.items()}, strict=True)
         self._frame_key = None
         return self
 
+    def build_encoders(self, seed: Optional[int] = None, autocast_dtype=None):
+        """Creates the CNN encoders of the step in front of the path (vanerf_b200/encoders.py; reference `geo_encoder`,
+        `tex_encoder`, src/model.py:630-654).  `load_state_dict` calls this when the checkpoint has `geo_encoder.*` entries;
+        `seed` fills them with name-keyed synthetic weights instead (no checkpoint is available offline)."""
+        from .encoders import Encoders, seeded_state_dict
+        m = self.kwargs
+        self.encoders = Encoders(m.get("geo_args"), m.get("tex_args"), int(m.get("ds_geo", 1)), int(m.get("ds_tex", 1))).eval()
+        if seed is not None:
+            self.encoders.geo_encoder.load_state_dict(seeded_state_dict(self.encoders.geo_encoder, seed), strict=True)
+            self.encoders.tex_encoder.load_state_dict(seeded_state_dict(self.encoders.tex_encoder, seed), strict=True)
+        self.encoders.to(self.device)
+        self.encoders.autocast_dtype = autocast_dtype
+        return self.encoders
+
     def attach_im_feat(self, im=None, return_val=False, feat_geo=None, feat_tex=None):
-        """The reference runs its CNN encoders here (src/model.py:700-738); they are outside this path, so the maps are
-        supplied by the caller."""
-        if feat_geo is None or feat_tex is None:
-            raise NotImplementedError("CNN encoders are out of scope: pass feat_geo=[g0,g1], feat_tex=...")
+        """src/model.py:700-709.  The maps are either supplied by the caller (`feat_geo=[g0, g1]`, `feat_tex=`) or computed from
+        the source images `im` (V,3,H,W in [0,1]) by the encoders (`build_encoders` / a checkpoint with encoder weights)."""
+        if feat_geo is None:
+            feat_geo = self.attach_geo_feat(im, return_val=True)
+        if feat_tex is None:
+            feat_tex = self.attach_tex_feat(im, return_val=True)
         self.feat_geo, self.feat_tex = feat_geo, feat_tex
         if return_val:
             return {"feat_geo": feat_geo, "feat_tex": feat_tex}
 
     def attach_geo_feat(self, im, return_val=False):
-        if self.feat_geo is None:
-            raise NotImplementedError("geo encoder (HGFilterV2) is out of scope: attach_im_feat(feat_geo=..., feat_tex=...)")
+        """src/model.py:711-724: average-pool `ds_geo` times, 2 x - 1, HGFilterV2 -> [geo0 (V,64,H/8,W/8), geo1 (V,8,H/2,W/2)]."""
+        if self.encoders is not None and im is not None:
+            self.feat_geo = self.encoders.encode_geo(im.to(self.device))
+        elif self.feat_geo is None:
+            raise L.VanerfError("no geometry feature maps: build_encoders() / load a checkpoint with geo_encoder.* weights and pass the "
+                                "source images, or attach_im_feat(feat_geo=[g0, g1], feat_tex=...)")
         return self.feat_geo if return_val else None
 
     def attach_tex_feat(self, im, return_val=False):
-        if self.feat_tex is None:
-            raise NotImplementedError("tex encoder (ResBlkEncoder) is out of scope: attach_im_feat(feat_geo=..., feat_tex=...)")
+        """src/model.py:726-738: average-pool `ds_tex` times, 2 x - 1, ResBlkEncoder -> (V,8,H/4,W/4)."""
+        if self.encoders is not None and im is not None:
+            self.feat_tex = self.encoders.encode_tex(im.to(self.device))
+        elif self.feat_tex is None:
+            raise L.VanerfError("no texture feature map: build_encoders() / load a checkpoint with tex_encoder.* weights and pass the "
+                                "source images, or attach_im_feat(feat_geo=[g0, g1], feat_tex=...)")
         return self.feat_tex if return_val else None
 
     def detach_im_feat(self):
