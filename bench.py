@@ -439,6 +439,27 @@ def main():
         launches = r.launches - launches0
         ms_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
         clk = clocks.stop() if rank == 0 else None
+        need = torch.tensor([1 if (rank == 0 and not clk["samples"]) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(need, 0)
+        if int(need.item()):
+            # the timed region was shorter than nvidia-smi's sampling period (many GPUs, short views): sample the clocks over an extra,
+            # untimed repetition of the very same steps
+            if rank == 0:
+                clocks = ClockSampler(local)
+                clocks.start()
+            t_end = time.perf_counter() + 1.0
+            go = torch.ones(1, device=dev)
+            while int(go.item()):
+                for _ in range(4):
+                    step()
+                torch.cuda.synchronize()
+                go.fill_(1 if time.perf_counter() < t_end else 0)
+                if world > 1:
+                    dist.broadcast(go, 0)
+            if rank == 0:
+                clk = clocks.stop()
+                clk["sampled"] = "extra untimed repetition of the same steps (timed region shorter than the sampling period)"
         # ---- instrumented pass (per-kernel-class CUDA events on the launching stream); not the headline
         r.timing(True)
         r.timing_read(reset=True)

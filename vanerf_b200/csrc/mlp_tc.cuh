@@ -93,6 +93,15 @@
 #ifndef TC_PREWAIT
 #define TC_PREWAIT 1                     // issuer waits for a step's weight chunks before it waits for the step's operands: -9 %
 #endif
+#ifndef TC_CODE_PAD
+#define TC_CODE_PAD 0
+#endif
+#define TC_STR2(x) #x
+#define TC_STR(x) TC_STR2(x)
+template <int N> __device__ __forceinline__ void tc_code_pad() {
+    if constexpr (N >= 16) { tc_code_pad<N / 2>(); tc_code_pad<N - N / 2>(); }
+    else if constexpr (N > 0) { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); tc_code_pad<N - 1>(); }
+}
 #ifndef TC_STAGGER
 #define TC_STAGGER 0                     // cycles between the start phases of CTA groups (blockIdx % TC_STAGGER_GROUPS)
 #endif
@@ -1089,6 +1098,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     unsigned char* smem = tc_smem_raw;
     TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#if TC_CODE_PAD
+    // developer experiment: shifts every later instruction by TC_CODE_PAD x 16 bytes (code-placement sensitivity of the kernel)
+    tc_code_pad<TC_CODE_PAD>();
+#endif
     const int V = A.V;
     const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
     constexpr int TPC = SPLIT ? 1 : TC_TILES;                  // tiles in flight per CTA
