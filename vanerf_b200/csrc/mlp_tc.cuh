@@ -119,12 +119,17 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
 #endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating,
                                          // 32 no proxy fence, 64 no waits for weight chunks, 128 no operand-image loads
+#ifndef TC_I9_REGS
+#define TC_I9_REGS 1                     // out_layer's last Linear (8 -> 1) in fp32 registers inside the epilogue of step I8: one round trip less per tile
+#endif
 enum TcStepId {
     ST_G1 = 0, ST_G2, ST_G3, ST_G4, ST_M0, ST_P0, ST_P1, ST_P2, ST_P3, ST_P4, ST_P5, ST_M1, ST_M2, ST_M3,
     ST_Q1, ST_Q2, ST_Q3, ST_T1, ST_T2, ST_T3, ST_T4, ST_I1, ST_I2, ST_I3, ST_I4, ST_I5, ST_I6, ST_I7, ST_I8, ST_I9,
     ST_COUNT
 };
 
+// steps that exist in the tables (the packer keeps their layers) but are evaluated in registers, never issued as MMAs
+constexpr bool tc_step_in_regs(int st);
 struct TcOp {
     uint32_t a_off;        // byte offset of the first K step inside the activation area (slot * 16 KB + (col0/16) * 32)
     uint32_t b_off;        // byte offset of the weight block inside its ring slot
@@ -133,6 +138,7 @@ struct TcOp {
     uint8_t nk, accum, chunk_rel, last_in_chunk;
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
+constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_I9_REGS && st == ST_I9); }
 struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
@@ -141,6 +147,7 @@ struct TcTables {                        // global memory (context-owned); copie
     alignas(16) float bias[TC_MAX_BIAS]; // read as float4 (offsets are multiples of 16 floats)
     alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
     alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
+    alignas(16) float out2w[8];          // IBRRenderingHead out_layer, last Linear (8 -> 1): fp32, in registers (TC_I9_REGS)
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
 };
@@ -246,7 +253,7 @@ constexpr TcProg tc_make_prog() {
         int acc = 0;
         for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
             P.cc_off[st] = (uint16_t)acc;
-            if (st != ST_G2) acc += P.steps[st].nchunks;
+            if (!tc_step_in_regs(st)) acc += P.steps[st].nchunks;
         }
         if (g == 0) P.cc_gm = (uint16_t)acc;
         else if (g == 1) P.cc_q = (uint16_t)acc;
@@ -272,7 +279,7 @@ constexpr TcLoadList tc_make_loads() {
     for (int g = 0; g < 4; ++g) {
         int cnt = 0;
         for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
-            if (st == ST_G2) continue;                       // attention layer 2 of GeoVisFusion runs in registers
+            if (tc_step_in_regs(st)) continue;               // attention layer 2 of GeoVisFusion (and out_layer's last Linear) run in registers
             for (int c = 0; c < kProg.steps[st].nchunks; ++c, ++n, ++cnt) {
                 L.src_off[n] = kProg.chunks[kProg.steps[st].chunk0 + c].src_off;
                 L.bytes[n] = kProg.chunks[kProg.steps[st].chunk0 + c].bytes;
@@ -469,12 +476,13 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
             int acc = 0;
             for (int st = grp_first[g]; st <= grp_last[g]; ++st) {
                 P.cc_off[st] = (uint16_t)acc;
-                if (st != ST_G2) acc += P.steps[st].nchunks;
+                if (!tc_step_in_regs(st)) acc += P.steps[st].nchunks;
             }
             *tot[g] = (uint16_t)acc;
         }
     }
     T.ani_al_abs = fabsf(ani_al);
+    for (int i = 0; i < 8; ++i) T.out2w[i] = src[L_OUT2]->w[i];
     for (int sc = 0; sc < 2; ++sc) {
         const vanerf_linear& L = *src[sc ? L_GEO8_AT1 : L_GEO_AT1];
         for (int j = 0; j < 3; ++j)
@@ -1080,7 +1088,10 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
         for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
         // the rendering head runs once per tile for all views
         ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
-        ISTEP(ST_I8, 0); ISTEP(ST_I9, 0);
+        ISTEP(ST_I8, 0);
+#if !TC_I9_REGS
+        ISTEP(ST_I9, 0);
+#endif
         cc += cc_i;
     }
 #undef ISTEP
@@ -1659,15 +1670,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
             t.step(ST_I8);
+#if TC_I9_REGS
+            // out_layer's last two layers end here: s_v = w2 . ELU(acc_v + b1) + b2 in fp32 registers (8 values per view)
+            if (h == 0) {
+                TC_VLOOP
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    if (v < V) {
+                        float x[8];
+                        t.ld8(16 * v, x);
+                        float sacc = BIASP(L_OUT2)[0];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) sacc = fmaf(t.tb->out2w[i], tc_act<TA_ELU>(x[i] + BIASP(L_OUT1)[i]), sacc);
+                        tc_set3(sv, v, (maskv == 0.0f) ? -1e4f : sacc);
+                    }
+                }
+            }
+#else
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
             t.step(ST_I9);
+#endif
             if ((TC_REC_EARLY & 8) && leader) {                 // every MMA of this tile has completed: the next tile's first images
                 const int pair_n = pair + gridDim.x;
                 prefetched = pair_n < n_pairs;
                 if (prefetched) load_geo(min(pair_n * TPC + tg, n_tiles - 1), 0);
             }
+#if !TC_I9_REGS
             if (h == 0) {
                 TC_VLOOP
                 for (int v = 0; v < TC_MAXV; ++v) {
@@ -1678,6 +1707,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     }
                 }
             }
+#endif
             // =========================================================== softmax blend + eval_func (src/model.py:1634-1635, 1140-1160)
             if (h == 0) {
                 float smax = -3.0e38f;
