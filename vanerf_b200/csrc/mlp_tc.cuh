@@ -119,6 +119,14 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
 #endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating,
                                          // 32 no proxy fence, 64 no waits for weight chunks, 128 no operand-image loads
+#ifndef TC_MERGE_G4
+#define TC_MERGE_G4 1                    // GeoVisFusion's last Linear (no bias, no activation) folded into the layers that consume it
+#endif                                   // (MLP layer 0's out64 columns, MLP layer 2's out8 columns): no step G4, one round trip less per view
+#define TC_M0_SLOT (TC_MERGE_G4 ? 4 : 0) // operand slot MLP layer 0 reads its 64 GeoVisFusion columns from (G3's output / G4's output)
+#define TC_PE_SLOT2 (TC_MERGE_G4 ? 0 : 4)   // third slot of the positional-encoding ring (slots 1, 2 and this one)
+#ifndef TC_I8_REGS
+#define TC_I8_REGS 0                     // out_layer's second Linear (16 -> 8) in fp32 registers too (implies TC_I9_REGS): no steps I8, I9
+#endif
 #ifndef TC_I9_REGS
 #define TC_I9_REGS 1                     // out_layer's last Linear (8 -> 1) in fp32 registers inside the epilogue of step I8: one round trip less per tile
 #endif
@@ -138,7 +146,8 @@ struct TcOp {
     uint8_t nk, accum, chunk_rel, last_in_chunk;
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
-constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_I9_REGS && st == ST_I9); }
+static_assert(!TC_I8_REGS || TC_I9_REGS, "TC_I8_REGS implies TC_I9_REGS");
+constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8); }
 struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
@@ -148,6 +157,7 @@ struct TcTables {                        // global memory (context-owned); copie
     alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
     alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
     alignas(16) float out2w[8];          // IBRRenderingHead out_layer, last Linear (8 -> 1): fp32, in registers (TC_I9_REGS)
+    alignas(16) float out1w[16 * 8];     // out_layer, second Linear (16 -> 8), input-major [i][j]: fp32, in registers (TC_I8_REGS)
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
 };
@@ -178,9 +188,9 @@ constexpr TcSpecC kSpecs[] = {
     {ST_G3, L_GEO_F0, 0, 0, 0, 0, 64, 0}, {ST_G3, L_GEO_F0, 1, 0, 0, 1, 64, 0}, {ST_G3, L_GEO_F0, 2, 0, 0, 1, 64, 0}, {ST_G3, L_GEO_F0, 3, 0, 0, 1, 16, 0},
     {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32, 0},
     {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64, 0}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16, 0},
-    {ST_M0, L_MLP0, 0, 0, 0, 0, 64, 0},
-    {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P2, L_MLP0, 4, 0, 0, 1, 64, 0},
-    {ST_P3, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P5, L_MLP0, 4, 0, 0, 1, 16, 0},
+    {ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, 64, 0},
+    {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P2, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 64, 0},
+    {ST_P3, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P5, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 16, 0},
     {ST_M1, L_MLP1, 1, 0, 0, 0, 64, 0}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64, 0},
     {ST_M2, L_MLP2, 4, 0, 0, 0, 64, 0}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64, 0}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16, 0},
     {ST_M3, L_MLP3, 1, 0, 0, 0, 64, 0}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64, 0},
@@ -337,12 +347,12 @@ static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
     add(ST_G4, L_GEO_F1, 4, 0, 0, 0, iota_map(0, 64));
     add(ST_G4, L_GEO8_F1, 3, 48, 64, 0, iota_map(0, 8, 16));
     // ---- MLPUNet layers1 (src/utils.py:822-852); layer 0 input = [PE 294 | out64], PE in per-keypoint groups of 8
-    add(ST_M0, L_MLP0, 0, 0, 0, 0, iota_map(294, 64));
+    add(ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, iota_map(294, 64));
     for (int s = 0; s < 6; ++s) {
         std::vector<int> m;
         for (int kl = 0; kl < (s < 5 ? 8 : 2); ++kl)
             for (int f = 0; f < 8; ++f) m.push_back(f < 7 ? f * NKPT + (8 * s + kl) : -1);
-        const int pslot[3] = {1, 2, 4};
+        const int pslot[3] = {1, 2, TC_PE_SLOT2};
         add(ST_P0 + s, L_MLP0, pslot[s % 3], 0, 0, 1, m);
     }
     add(ST_M1, L_MLP1, 1, 0, 0, 0, iota_map(0, 64));
@@ -398,10 +408,49 @@ static inline uint16_t f2bf_host(float f) {
 }
 
 // Builds the step / op / chunk tables and the bf16 weight images (blob) from the folded fp32 layers.
-static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T, TcProg& P, std::vector<uint16_t>& blob,
+static void tc_build(const vanerf_linear* const* src_in, float ani_al, TcTables& T, TcProg& P, std::vector<uint16_t>& blob,
                      std::vector<uint16_t>* blob_lo = nullptr) {
     std::vector<std::vector<TcOpSpec>> st;
     tc_build_script(st);
+#if TC_MERGE_G4
+    // Fold GeoVisFusion's second fused Linear F (c x c, src/networks.py:101-104: no bias, no activation behind it) into its two
+    // consumers: MLP layer 0 reads out64 in its input columns [294, 358), MLP layer 2 reads out8 in [128, 136), so
+    // W[:, cols] <- W[:, cols] . F and the layers take ReLU(fused layer 1) instead (products in double, rounded once).
+    const vanerf_linear* folded[L_COUNT];
+    for (int l = 0; l < L_COUNT; ++l) folded[l] = src_in[l];
+    std::vector<float> wf[2], bf[2];
+    vanerf_linear lf[2];
+    {
+        const int consumer[2] = {L_MLP0, L_MLP2}, inner[2] = {L_GEO_F1, L_GEO8_F1}, col0[2] = {294, 128};
+        for (int q = 0; q < 2; ++q) {
+            const vanerf_linear& C = *src_in[consumer[q]];
+            const vanerf_linear& F = *src_in[inner[q]];
+            const int c = F.out_dim;
+            wf[q].assign(C.w, C.w + (size_t)C.out_dim * C.in_dim);
+            if (C.b) bf[q].assign(C.b, C.b + C.out_dim);
+            for (int n = 0; n < C.out_dim; ++n) {
+                for (int j = 0; j < F.in_dim; ++j) {
+                    double acc = 0.0;
+                    for (int i = 0; i < c; ++i) acc += (double)C.w[(size_t)n * C.in_dim + col0[q] + i] * (double)F.w[(size_t)i * F.in_dim + j];
+                    wf[q][(size_t)n * C.in_dim + col0[q] + j] = (float)acc;
+                }
+                if (F.b) {             // not the case in the reference (bias=False); kept exact if a checkpoint has one
+                    double acc = C.b ? (double)C.b[n] : 0.0;
+                    for (int i = 0; i < c; ++i) acc += (double)C.w[(size_t)n * C.in_dim + col0[q] + i] * (double)F.b[i];
+                    if (bf[q].empty()) bf[q].assign(C.out_dim, 0.0f);
+                    bf[q][n] = (float)acc;
+                }
+            }
+            lf[q] = C;
+            lf[q].w = wf[q].data();
+            lf[q].b = bf[q].empty() ? nullptr : bf[q].data();
+            folded[consumer[q]] = &lf[q];
+        }
+    }
+    const vanerf_linear* const* src = folded;
+#else
+    const vanerf_linear* const* src = src_in;
+#endif
     memset(&T, 0, sizeof(T));
     memset(&P, 0, sizeof(P));
     blob.clear();
@@ -483,6 +532,8 @@ static void tc_build(const vanerf_linear* const* src, float ani_al, TcTables& T,
     }
     T.ani_al_abs = fabsf(ani_al);
     for (int i = 0; i < 8; ++i) T.out2w[i] = src[L_OUT2]->w[i];
+    for (int i = 0; i < 16; ++i)
+        for (int j = 0; j < 8; ++j) T.out1w[i * 8 + j] = src[L_OUT1]->w[(size_t)j * 16 + i];
     for (int sc = 0; sc < 2; ++sc) {
         const vanerf_linear& L = *src[sc ? L_GEO8_AT1 : L_GEO_AT1];
         for (int j = 0; j < 3; ++j)
@@ -1078,7 +1129,10 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
         if (*reinterpret_cast<volatile int*>(sh->abort_flag)) break;
 #pragma unroll 1
         for (int v = 0; v < V; ++v, cc += cc_gm) {
-            ISTEP(ST_G1, 0); ISTEP(ST_G3, 0); ISTEP(ST_G4, 0);
+            ISTEP(ST_G1, 0); ISTEP(ST_G3, 0);
+#if !TC_MERGE_G4
+            ISTEP(ST_G4, 0);
+#endif
             ISTEP(ST_M0, -1); ISTEP(ST_P0, 1); ISTEP(ST_P1, 2); ISTEP(ST_P2, 3); ISTEP(ST_P3, 1); ISTEP(ST_P4, 2); ISTEP(ST_P5, 0);
             ISTEP(ST_M1, 0); ISTEP(ST_M2, 0); ISTEP(ST_M3, 0);
         }
@@ -1088,9 +1142,11 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
         for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
         // the rendering head runs once per tile for all views
         ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
+#if !TC_I8_REGS
         ISTEP(ST_I8, 0);
 #if !TC_I9_REGS
         ISTEP(ST_I9, 0);
+#endif
 #endif
         cc += cc_i;
     }
@@ -1251,16 +1307,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 t.step(ST_G3);
                 EPI(TA_RELU, 32 * h, 2, NOBIAS, 4, 4 * h);
                 if (h == 0) EPI(TA_RELU, 64, 1, NOBIAS, 3, 6);
+#if !TC_MERGE_G4
                 // ---- G4: fused layer 2 -> out64 (slot 0), out8 (slot 3 cols 48..63)
                 t.step(ST_G4);
                 EPI(TA_NONE, 32 * h, 2, NOBIAS, 0, 4 * h);
                 if (h == 1) EPI(TA_NONE, 64, 1, NOBIAS, 3, 6);
+#endif
+                // (TC_MERGE_G4: fused layer 2 is linear, bias-free and feeds only Linear layers, so its matrix is folded into their
+                //  weights when they are packed - tc_build - and MLP layer 0 / 2 read G3's ReLU outputs in slot 4 / slot 3 directly)
                 // ---- MLP layer 0: out64 part, then the positional encoding in 6 operand slots through a 3-slot ring
                 t.issue(ST_M0, -1);
 #pragma unroll 1
                 for (int s = 0; s < 6; ++s) {
                     const int ps = s % 3;
-                    const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : 4;
+                    const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : TC_PE_SLOT2;
                     if (s >= 3) {
                         tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + s);
                         t.pfree_bits ^= 1u << ps;
@@ -1666,11 +1726,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 }
             }
             t.step(ST_I7);
+#if TC_I8_REGS
+            // out_layer's last two Linears (16 -> 8 -> 1, src/model.py:1588-1593) in fp32 registers: s_v = w2 . ELU(W1 ELU(acc_v + b0) + b1) + b2.
+            // One thread per row takes all views (the softmax below needs the three scores in one thread); two round trips less
+            // per tile and no bf16 rounding behind out_layer's first Linear.
+            if (h == 0) {
+                TC_VLOOP
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    if (v < V) {
+                        float x[16], y[8];
+                        t.ld16(16 * v, x);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_OUT0)[i]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y[j] = BIASP(L_OUT1)[j];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+#if TC_F32X2
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                const float2 r2 = __ffma2_rn(make_float2(t.tb->out1w[i * 8 + j], t.tb->out1w[i * 8 + j + 1]), make_float2(x[i], x[i]),
+                                                             make_float2(y[j], y[j + 1]));
+                                y[j] = r2.x; y[j + 1] = r2.y;
+                            }
+#else
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) y[j] = fmaf(t.tb->out1w[i * 8 + j], x[i], y[j]);
+#endif
+                        }
+                        float sacc = BIASP(L_OUT2)[0];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sacc = fmaf(t.tb->out2w[j], tc_act<TA_ELU>(y[j]), sacc);
+                        tc_set3(sv, v, (maskv == 0.0f) ? -1e4f : sacc);
+                    }
+                }
+            }
+#else
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
             t.step(ST_I8);
-#if TC_I9_REGS
+#endif
+#if TC_I8_REGS
+#elif TC_I9_REGS
             // out_layer's last two layers end here: s_v = w2 . ELU(acc_v + b1) + b2 in fp32 registers (8 values per view)
             if (h == 0) {
                 TC_VLOOP
