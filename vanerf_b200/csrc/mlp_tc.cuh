@@ -124,6 +124,9 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
 #endif                                   // (MLP layer 0's out64 columns, MLP layer 2's out8 columns): no step G4, one round trip less per view
 #define TC_M0_SLOT (TC_MERGE_G4 ? 4 : 0) // operand slot MLP layer 0 reads its 64 GeoVisFusion columns from (G3's output / G4's output)
 #define TC_PE_SLOT2 (TC_MERGE_G4 ? 0 : 4)   // third slot of the positional-encoding ring (slots 1, 2 and this one)
+#ifndef TC_PAIR_REGS
+#define TC_PAIR_REGS 0                   // bit mask (1: step Q3, 2: step I6; measured slower than the MMA round trips: off): Linears with <= 2 outputs behind a row-split epilogue (density head 64 -> 2: step Q3, vis2 32 -> 1: step I6)
+#endif                                   // as fp32 partial dot products in the two threads of a row, exchanged through TMEM at a 64-thread named barrier
 #ifndef TC_I8_REGS
 #define TC_I8_REGS 0                     // out_layer's second Linear (16 -> 8) in fp32 registers too (implies TC_I9_REGS): no steps I8, I9
 #endif
@@ -147,7 +150,7 @@ struct TcOp {
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
 static_assert(!TC_I8_REGS || TC_I9_REGS, "TC_I8_REGS implies TC_I9_REGS");
-constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8); }
+constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8) || ((TC_PAIR_REGS & 1) && st == ST_Q3) || ((TC_PAIR_REGS & 2) && st == ST_I6); }
 struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
@@ -157,6 +160,8 @@ struct TcTables {                        // global memory (context-owned); copie
     alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
     alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
     alignas(16) float out2w[8];          // IBRRenderingHead out_layer, last Linear (8 -> 1): fp32, in registers (TC_I9_REGS)
+    alignas(16) float post2w[2 * 64];    // density head, last Linear (64 -> 2): fp32, in registers (TC_PAIR_REGS)
+    alignas(16) float vis2w[32];         // IBRRenderingHead vis2, last Linear (32 -> 1): fp32, in registers (TC_PAIR_REGS)
     alignas(16) float out1w[16 * 8];     // out_layer, second Linear (16 -> 8), input-major [i][j]: fp32, in registers (TC_I8_REGS)
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
@@ -532,6 +537,8 @@ static void tc_build(const vanerf_linear* const* src_in, float ani_al, TcTables&
     }
     T.ani_al_abs = fabsf(ani_al);
     for (int i = 0; i < 8; ++i) T.out2w[i] = src[L_OUT2]->w[i];
+    for (int i = 0; i < 128; ++i) T.post2w[i] = src[L_POST2]->w[i];
+    for (int i = 0; i < 32; ++i) T.vis2w[i] = src[L_VIS2_1]->w[i];
     for (int i = 0; i < 16; ++i)
         for (int j = 0; j < 8; ++j) T.out1w[i * 8 + j] = src[L_OUT1]->w[(size_t)j * 16 + i];
     for (int sc = 0; sc < 2; ++sc) {
@@ -557,7 +564,7 @@ static bool tc_program_matches(const TcProg& P) {
 }
 
 static_assert(TC_TAB_PARAM || sizeof(TcTables) <= TC_TAB_BYTES, "TC_TAB_BYTES too small");
-static_assert(sizeof(TcTables) <= 8192, "TcTables travels as a kernel parameter");
+static_assert(sizeof(TcTables) <= 16384, "TcTables travels as a kernel parameter (limit 32 764 bytes together with TcArgs)");
 static_assert(sizeof(TcProg) <= 8192, "TcProg must stay a small part of constant memory");
 // ================================================================================================ device
 // Optional cycle trace of CTA 0 / thread 0 (vanerf_tc_profile), compiled in only with -DVANERF_TC_TRACE: entries
@@ -920,6 +927,17 @@ struct TcTile {
         TC_PROF(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
+    // The two threads of a row (warps w and w + 4 of the tile group: same TMEM lanes) swap up to 8 fp32 values: each stores its own
+    // into TMEM columns only it has read (`col_mine`), the two warps meet at their named barrier (ids 3..10), each loads the other's.
+    // Every use is followed by a step publish of both warps before the columns are written again, so one scratch area suffices.
+    __device__ __forceinline__ void pair_exchange8(int col_mine, int col_theirs, const float (&mine)[8], float (&theirs)[8]) const {
+        st8(col_mine, mine);
+        tc::tmem_st_wait();
+        tc::tcgen05_fence_before();
+        tc::named_bar_sync(3 + 4 * tg + (int)((threadIdx.x >> 5) & 3), 64);
+        tc::tcgen05_fence_after();
+        ld8(col_theirs, theirs);
+    }
     // multiply the 8 values of a chunk by per-element gates (fp32 product, one rounding back to bf16 [hi + lo])
     template <bool SPLIT>
     __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
@@ -1136,12 +1154,19 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
             ISTEP(ST_M0, -1); ISTEP(ST_P0, 1); ISTEP(ST_P1, 2); ISTEP(ST_P2, 3); ISTEP(ST_P3, 1); ISTEP(ST_P4, 2); ISTEP(ST_P5, 0);
             ISTEP(ST_M1, 0); ISTEP(ST_M2, 0); ISTEP(ST_M3, 0);
         }
-        ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0); ISTEP(ST_Q3, 0);
+        ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0);
+#if !(TC_PAIR_REGS & 1)
+        ISTEP(ST_Q3, 0);
+#endif
         cc += cc_q;
 #pragma unroll 1
         for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
         // the rendering head runs once per tile for all views
-        ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0);
+        ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0);
+#if !(TC_PAIR_REGS & 2)
+        ISTEP(ST_I6, 0);
+#endif
+        ISTEP(ST_I7, 0);
 #if !TC_I8_REGS
         ISTEP(ST_I8, 0);
 #if !TC_I9_REGS
@@ -1458,15 +1483,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 split8(x, lat_a, lat_al);
             }
             t.step(ST_Q2);
+            float o0, o1;
+#if TC_PAIR_REGS & 1
+            {   // last Linear of the density head (64 -> 2, src/utils.py:687-719) on the 32 Softplus outputs each thread of the row holds
+                float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, other[8];
+                const float* w0 = t.tb->post2w + 32 * h;
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    float x[16];
+                    t.ld16(32 * h + 16 * g, x);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = tc_act<TA_SOFTPLUS>(x[i] + BIASP(L_POST1)[32 * h + 16 * g + i]);
+                        part[0] = fmaf(w0[16 * g + i], a, part[0]);
+                        part[1] = fmaf(w0[64 + 16 * g + i], a, part[1]);
+                    }
+                }
+                t.pair_exchange8(32 * h, 32 * (1 - h), part, other);
+                o0 = (h ? other[0] + part[0] : part[0] + other[0]) + BIASP(L_POST2)[0];      // same order in both threads
+                o1 = (h ? other[1] + part[1] : part[1] + other[1]) + BIASP(L_POST2)[1];
+            }
+#else
             EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST1) + 32 * h, 0, 4 * h);
             t.step(ST_Q3);
-            float o0, o1;
             {
                 float x[8];
                 t.ld8(0, x);
                 o0 = x[0] + BIASP(L_POST2)[0];
                 o1 = x[1] + BIASP(L_POST2)[1];
             }
+#endif
             // =========================================================== texture branch per view
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
@@ -1702,15 +1748,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             tc::tmem_st_wait();
             t.step(ST_I5);
+#if TC_PAIR_REGS & 2
+            float vsum[TC_MAXV];
+            {   // vis2's last Linear (32 -> 1, src/model.py:1582-1586) on the 16 ELU outputs per view each thread of the row holds
+                float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, other[8];
+                TC_VLOOP
+                for (int v = 0; v < TC_MAXV; ++v) {
+                    if (v < V) {
+                        float x[16];
+                        t.ld16(48 * v + 16 * h, x);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc = fmaf(t.tb->vis2w[16 * h + i], tc_act<TA_ELU>(x[i] + BIASP(L_VIS2_0)[16 * h + i]), acc);
+                        part[0] = v == 0 ? acc : part[0]; part[1] = v == 1 ? acc : part[1]; part[2] = v == 2 ? acc : part[2];
+                    }
+                }
+                t.pair_exchange8(16 * h, 16 * (1 - h), part, other);
+#pragma unroll
+                for (int v = 0; v < TC_MAXV; ++v) vsum[v] = h ? other[v] + part[v] : part[v] + other[v];
+            }
+#else
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V) tc_epi_store<TA_ELU, 1, SPLIT>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I6);
+#endif
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
                 if (v < V) {
                     float vv[8], x[16];
+#if TC_PAIR_REGS & 2
+                    vv[0] = tc_sel3(vsum, v);
+#else
                     t.ld8(48 * v, vv);
+#endif
                     t.ld16(160 + 32 * v + 16 * h, x);
                     const float vis2 = tc_act<TA_SIGMOID>(vv[0] + BIASP(L_VIS2_1)[0]) * maskv;
                     // out_layer input [x 32 | vis | ray_diff 4] -> slot 2+v cols 0..47
