@@ -87,9 +87,12 @@ class CompositeFn(torch.autograd.Function):
         R, S = z.shape
         d_rgba = torch.zeros((R, S, 5), dtype=torch.float32, device=z.device)
         d_beta = torch.zeros((1,), dtype=torch.float32, device=z.device)
-        p = lambda t: r._ptr(t.contiguous()) if t is not None else None
-        st = r.lib.dll.vanerf_composite_bwd(r.ctx, r._ptr(rgba), r._ptr(z), r._ptr(mesh_sdf), R, S, ctx.b, p(g_color), p(g_alpha), p(g_depth),
-                                            p(g_sdf), r._ptr(d_rgba), r._ptr(d_beta), r.stream)
+        # contiguous copies of the incoming gradients must stay referenced until the call has been issued: a pointer taken from a
+        # temporary dangles as soon as the temporary is released (its block is handed to the next allocation)
+        keep = [t.contiguous() if t is not None else None for t in (g_color, g_alpha, g_depth, g_sdf)]
+        p = lambda t: r._ptr(t) if t is not None else None
+        st = r.lib.dll.vanerf_composite_bwd(r.ctx, r._ptr(rgba), r._ptr(z), r._ptr(mesh_sdf), R, S, ctx.b, p(keep[0]), p(keep[1]), p(keep[2]),
+                                            p(keep[3]), r._ptr(d_rgba), r._ptr(d_beta), r.stream)
         r.lib.check(r.ctx, st, "vanerf_composite_bwd")
         return None, d_rgba, None, None, d_beta
 
