@@ -113,7 +113,7 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
                                          // 1 next view's geometry images after M3, 2 first texture image after Q1, 4 next texture image after T3, 8 next tile's images after I9
 #endif
 #ifndef TC_PE_UNROLL
-#define TC_PE_UNROLL 0                   // the four keypoints of a PE step as independent instruction streams (the rolled loop is one dependent chain per keypoint)
+#define TC_PE_UNROLL TC_PMERGE                 // the four keypoints of a PE step as independent instruction streams (the rolled loop is one dependent chain per keypoint)
 #endif
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
@@ -124,6 +124,9 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
 #endif                                   // (MLP layer 0's out64 columns, MLP layer 2's out8 columns): no step G4, one round trip less per view
 #define TC_M0_SLOT (TC_MERGE_G4 ? 4 : 0) // operand slot MLP layer 0 reads its 64 GeoVisFusion columns from (G3's output / G4's output)
 #define TC_PE_SLOT2 (TC_MERGE_G4 ? 0 : 4)   // third slot of the positional-encoding ring (slots 1, 2 and this one)
+#ifndef TC_PMERGE
+#define TC_PMERGE 0                      // MLP layer 0 in two publishes instead of seven: step M0 = [out64 | PE keypoints 0-15, 40-41] with a
+#endif                                   // ring-slot commit behind each of the two PE slots, step P0 = [PE keypoints 16-39] (needs TC_MERGE_G4)
 #ifndef TC_PAIR_REGS
 #define TC_PAIR_REGS 0                   // bit mask (1: step Q3, 2: step I6; measured slower than the MMA round trips: off): Linears with <= 2 outputs behind a row-split epilogue (density head 64 -> 2: step Q3, vis2 32 -> 1: step I6)
 #endif                                   // as fp32 partial dot products in the two threads of a row, exchanged through TMEM at a 64-thread named barrier
@@ -150,7 +153,10 @@ struct TcOp {
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
 static_assert(!TC_I8_REGS || TC_I9_REGS, "TC_I8_REGS implies TC_I9_REGS");
-constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8) || ((TC_PAIR_REGS & 1) && st == ST_Q3) || ((TC_PAIR_REGS & 2) && st == ST_I6); }
+static_assert(!TC_PMERGE || TC_MERGE_G4, "TC_PMERGE needs slot 0 for the positional encoding (TC_MERGE_G4)");
+// ring-slot barrier (1..3, 0 = none) an op of a step commits to when its MMAs have been issued (TC_PMERGE: the two PE slots of step M0)
+__host__ __device__ constexpr int tc_op_pfree(int st, int op) { return (TC_PMERGE && st == ST_M0 && (op == 1 || op == 2)) ? op : 0; }
+constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_PMERGE && st >= ST_P1 && st <= ST_P5) || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8) || ((TC_PAIR_REGS & 1) && st == ST_Q3) || ((TC_PAIR_REGS & 2) && st == ST_I6); }
 struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
@@ -194,8 +200,13 @@ constexpr TcSpecC kSpecs[] = {
     {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32, 0},
     {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64, 0}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16, 0},
     {ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, 64, 0},
+#if TC_PMERGE
+    {ST_M0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_M0, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_M0, L_MLP0, 3, 0, 0, 1, 16, 0},       // PE blocks 0, 1, 5
+    {ST_P0, L_MLP0, 0, 0, 0, 1, 64, 0}, {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P0, L_MLP0, 2, 0, 0, 1, 64, 0},       // PE blocks 2, 3, 4
+#else
     {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P2, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 64, 0},
     {ST_P3, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P5, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 16, 0},
+#endif
     {ST_M1, L_MLP1, 1, 0, 0, 0, 64, 0}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64, 0},
     {ST_M2, L_MLP2, 4, 0, 0, 0, 64, 0}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64, 0}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16, 0},
     {ST_M3, L_MLP3, 1, 0, 0, 0, 64, 0}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64, 0},
@@ -353,12 +364,18 @@ static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
     add(ST_G4, L_GEO8_F1, 3, 48, 64, 0, iota_map(0, 8, 16));
     // ---- MLPUNet layers1 (src/utils.py:822-852); layer 0 input = [PE 294 | out64], PE in per-keypoint groups of 8
     add(ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, iota_map(294, 64));
-    for (int s = 0; s < 6; ++s) {
+    for (int q = 0; q < 6; ++q) {
+#if TC_PMERGE
+        const int order[6] = {0, 1, 5, 2, 3, 4}, slot_of[6] = {1, 2, 0, 1, 2, 3};      // PE block -> operand slot; blocks 0, 1, 5 ride in step M0
+        const int s = order[q], step = q < 3 ? ST_M0 : ST_P0, slot = slot_of[s];
+#else
+        const int pslot[3] = {1, 2, TC_PE_SLOT2};
+        const int s = q, step = ST_P0 + s, slot = pslot[s % 3];
+#endif
         std::vector<int> m;
         for (int kl = 0; kl < (s < 5 ? 8 : 2); ++kl)
             for (int f = 0; f < 8; ++f) m.push_back(f < 7 ? f * NKPT + (8 * s + kl) : -1);
-        const int pslot[3] = {1, 2, TC_PE_SLOT2};
-        add(ST_P0 + s, L_MLP0, pslot[s % 3], 0, 0, 1, m);
+        add(step, L_MLP0, slot, 0, 0, 1, m);
     }
     add(ST_M1, L_MLP1, 1, 0, 0, 0, iota_map(0, 64));
     add(ST_M1, L_MLP1, 2, 0, 0, 1, iota_map(64, 64));
@@ -701,7 +718,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
 // Whole warp, converged; `lead` = the elected lane that executes the MMAs and commits.
 template <int ST, int I, bool SPLIT>
 __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint32_t slot_i, uint64_t bd_slot_lo, uint32_t slot_lo, TcShared* sh,
-                                            uint64_t ad_base, uint64_t bd_base, uint32_t tmem, bool lead) {
+                                            uint64_t ad_base, uint64_t bd_base, uint32_t tmem, bool lead, int tg) {
     constexpr TcStep S = kProg.steps[ST];
     constexpr TcOp op = kProg.ops[S.op0 + I];
     constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
@@ -741,8 +758,10 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
             tc::umma_commit(&sh->wempty[slot_i]);
             if (SPLIT) tc::umma_commit(&sh->wempty[slot_lo]);
         }
+        constexpr int pf = tc_op_pfree(ST, I);
+        if (pf) tc::umma_commit(&sh->pfree[tg][pf > 0 ? pf - 1 : 0]);
     }
-    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1, SPLIT>(cc, bd_slot, slot_i, bd_slot_lo, slot_lo, sh, ad_base, bd_base, tmem, lead);
+    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1, SPLIT>(cc, bd_slot, slot_i, bd_slot_lo, slot_lo, sh, ad_base, bd_base, tmem, lead, tg);
 }
 // Waits for every weight chunk of step ST (TC_PREWAIT): done BEFORE the wait for the step's operands, because the weights
 // are streamed a step ahead and have normally landed long before the tile's epilogue publishes; the ~100-cycle
@@ -784,7 +803,7 @@ __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, Tc
     // kernel is draining and results are discarded): otherwise the compiler computes the descriptors of all 140-odd
     // MMAs ahead of the waits and spills them to local memory.
     const uint32_t never = ok ? 0u : 16u;
-    tc_issue_op<ST, 0, SPLIT>(cc_base + cc_off, 0, 0, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead);
+    tc_issue_op<ST, 0, SPLIT>(cc_base + cc_off, 0, 0, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead, tg);
     if (lead) {
         if (COMMIT == 0) tc::umma_commit(&sh->acc_bar[tg]);
         else if (COMMIT > 0) tc::umma_commit(&sh->pfree[tg][COMMIT > 0 ? COMMIT - 1 : 0]);
@@ -1151,7 +1170,11 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
 #if !TC_MERGE_G4
             ISTEP(ST_G4, 0);
 #endif
+#if TC_PMERGE
+            ISTEP(ST_M0, -1); ISTEP(ST_P0, 0);
+#else
             ISTEP(ST_M0, -1); ISTEP(ST_P0, 1); ISTEP(ST_P1, 2); ISTEP(ST_P2, 3); ISTEP(ST_P3, 1); ISTEP(ST_P4, 2); ISTEP(ST_P5, 0);
+#endif
             ISTEP(ST_M1, 0); ISTEP(ST_M2, 0); ISTEP(ST_M3, 0);
         }
         ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0);
@@ -1340,16 +1363,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
                 // (TC_MERGE_G4: fused layer 2 is linear, bias-free and feeds only Linear layers, so its matrix is folded into their
                 //  weights when they are packed - tc_build - and MLP layer 0 / 2 read G3's ReLU outputs in slot 4 / slot 3 directly)
-                // ---- MLP layer 0: out64 part, then the positional encoding in 6 operand slots through a 3-slot ring
-                t.issue(ST_M0, -1);
-#pragma unroll 1
-                for (int s = 0; s < 6; ++s) {
-                    const int ps = s % 3;
-                    const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : TC_PE_SLOT2;
-                    if (s >= 3) {
-                        tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + s);
-                        t.pfree_bits ^= 1u << ps;
-                    }
+                // ---- MLP layer 0: out64 part + the positional encoding (42 keypoints x 8 columns = six operand blocks, src/spatial.py:59-117)
+                // PE block s (keypoints 8 s .. 8 s + 7; block 5: two keypoints) -> operand slot `pslot`, this thread's keypoints 8 s + 2 j + h
+                auto gen_pe = [&](int s, int pslot) {
                     const int nk = s < 5 ? 4 : 1;
 #if TC_PE_UNROLL
 #pragma unroll
@@ -1376,6 +1392,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                         else t.st_chunk(pslot, 2 * j + h, make_uint4(tc_pack_scaled(dz, s1, w), tc_pack_scaled(c1, s2, w),
                                                                     tc_pack_scaled(c2, s4, w), tc::pack_bf16(c4 * w, 0.0f)));
                     }
+                };
+#if TC_PMERGE
+                // two publishes: [out64 (slot 4) | blocks 0, 1 (slots 1, 2) | block 5 (slot 3 cols 0..15)], then [blocks 2, 3, 4 (slots 0, 1, 2)];
+                // the issuer commits the ring-slot barriers 0 / 1 right behind the MMAs of blocks 0 / 1, so blocks 3 / 4 are generated
+                // while the rest of the first step is still running
+                gen_pe(0, 1);
+                gen_pe(1, 2);
+                gen_pe(5, 3);
+                t.issue(ST_M0, -1);
+                gen_pe(2, 0);
+#pragma unroll 1
+                for (int ps = 0; ps < 2; ++ps) {
+                    tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + ps);
+                    t.pfree_bits ^= 1u << ps;
+                    gen_pe(3 + ps, 1 + ps);
+                }
+                t.step(ST_P0);
+#else
+                // seven publishes: out64, then the six blocks through a 3-slot ring
+                t.issue(ST_M0, -1);
+#pragma unroll 1
+                for (int s = 0; s < 6; ++s) {
+                    const int ps = s % 3;
+                    const int pslot = ps == 0 ? 1 : ps == 1 ? 2 : TC_PE_SLOT2;
+                    if (s >= 3) {
+                        tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + s);
+                        t.pfree_bits ^= 1u << ps;
+                    }
+                    gen_pe(s, pslot);
                     // P0..P4 commit to their ring-slot barrier, P5 completes the accumulator
                     t.issue(ST_P0 + s, s < 5 ? 1 + ps : 0);
                 }
@@ -1386,6 +1431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 510 + ps);
                     t.pfree_bits ^= 1u << ps;
                 }
+#endif
 #if TC_ROLL_MLP
                 // h0 -> slots 1, 2; h1 -> slots 4, 0; h2 -> slots 1, 2: one copy of the 64-column Softplus epilogue
 #pragma unroll 1
