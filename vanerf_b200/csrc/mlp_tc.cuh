@@ -93,28 +93,13 @@
 #ifndef TC_PREWAIT
 #define TC_PREWAIT 1                     // issuer waits for a step's weight chunks before it waits for the step's operands: -9 %
 #endif
-#ifndef TC_CODE_PAD
-#define TC_CODE_PAD 0
-#endif
-#define TC_STR2(x) #x
-#define TC_STR(x) TC_STR2(x)
-template <int N> __device__ __forceinline__ void tc_code_pad() {
-    if constexpr (N >= 16) { tc_code_pad<N / 2>(); tc_code_pad<N - N / 2>(); }
-    else if constexpr (N > 0) { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); tc_code_pad<N - 1>(); }
-}
-#ifndef TC_STAGGER
-#define TC_STAGGER 0                     // cycles between the start phases of CTA groups (blockIdx % TC_STAGGER_GROUPS)
-#endif
-#ifndef TC_STAGGER_GROUPS
-#define TC_STAGGER_GROUPS 16
-#endif
-#ifndef TC_REC_EARLY
-#define TC_REC_EARLY 0                   // bit mask: operand images requested one step before they are needed (see load_geo / load_tex):
-                                         // 1 next view's geometry images after M3, 2 first texture image after Q1, 4 next texture image after T3, 8 next tile's images after I9
-#endif
-#ifndef TC_PE_UNROLL
-#define TC_PE_UNROLL TC_PMERGE                 // the four keypoints of a PE step as independent instruction streams (the rolled loop is one dependent chain per keypoint)
-#endif
+// Measured and dropped at the end of round 2 (the variants are in the history of this file): operand images
+// requested one step before they are needed (80.1 .. 81.4 vs 79.2 ms per view); CTAs started out of phase (no effect); the four
+// keypoints of a positional-encoding block as independent instruction streams (+2 %: the blocks are paced by the issuer, not by their
+// generation); MLP layer 0 in two publishes with per-slot ring commits instead of seven (75.5 vs 74.5); out_layer's second Linear in
+// registers on one thread per row (77.2 vs 74.5); the 64 -> 2 and 32 -> 1 Linears as partial dot products swapped between the two
+// threads of a row through TMEM at a 64-thread named barrier (74.8 / 74.6 vs 74.3: a pair exchange costs what the MMA round trip
+// costs); 8 .. 1 000 padding instructions in front of the body (+-0.7 %: code placement is the noise floor of all of these).
 #ifndef TC_ABLATE
 #define TC_ABLATE 0                      // developer timing experiments (results are wrong when non-zero): 1 softplus -> relu,
 #endif                                   // 2 PE without MUFU, 4 one K step per MMA op, 8 ELU / sigmoid -> identity, 16 no gating,
@@ -124,15 +109,6 @@ template <int N> __device__ __forceinline__ void tc_code_pad() {
 #endif                                   // (MLP layer 0's out64 columns, MLP layer 2's out8 columns): no step G4, one round trip less per view
 #define TC_M0_SLOT (TC_MERGE_G4 ? 4 : 0) // operand slot MLP layer 0 reads its 64 GeoVisFusion columns from (G3's output / G4's output)
 #define TC_PE_SLOT2 (TC_MERGE_G4 ? 0 : 4)   // third slot of the positional-encoding ring (slots 1, 2 and this one)
-#ifndef TC_PMERGE
-#define TC_PMERGE 0                      // MLP layer 0 in two publishes instead of seven: step M0 = [out64 | PE keypoints 0-15, 40-41] with a
-#endif                                   // ring-slot commit behind each of the two PE slots, step P0 = [PE keypoints 16-39] (needs TC_MERGE_G4)
-#ifndef TC_PAIR_REGS
-#define TC_PAIR_REGS 0                   // bit mask (1: step Q3, 2: step I6; measured slower than the MMA round trips: off): Linears with <= 2 outputs behind a row-split epilogue (density head 64 -> 2: step Q3, vis2 32 -> 1: step I6)
-#endif                                   // as fp32 partial dot products in the two threads of a row, exchanged through TMEM at a 64-thread named barrier
-#ifndef TC_I8_REGS
-#define TC_I8_REGS 0                     // out_layer's second Linear (16 -> 8) in fp32 registers too (implies TC_I9_REGS): no steps I8, I9
-#endif
 #ifndef TC_I9_REGS
 #define TC_I9_REGS 1                     // out_layer's last Linear (8 -> 1) in fp32 registers inside the epilogue of step I8: one round trip less per tile
 #endif
@@ -152,11 +128,7 @@ struct TcOp {
     uint8_t nk, accum, chunk_rel, last_in_chunk;
 };
 struct TcStep { uint16_t op0, nops, chunk0, nchunks; };
-static_assert(!TC_I8_REGS || TC_I9_REGS, "TC_I8_REGS implies TC_I9_REGS");
-static_assert(!TC_PMERGE || TC_MERGE_G4, "TC_PMERGE needs slot 0 for the positional encoding (TC_MERGE_G4)");
-// ring-slot barrier (1..3, 0 = none) an op of a step commits to when its MMAs have been issued (TC_PMERGE: the two PE slots of step M0)
-__host__ __device__ constexpr int tc_op_pfree(int st, int op) { return (TC_PMERGE && st == ST_M0 && (op == 1 || op == 2)) ? op : 0; }
-constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_PMERGE && st >= ST_P1 && st <= ST_P5) || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9) || (TC_I8_REGS && st == ST_I8) || ((TC_PAIR_REGS & 1) && st == ST_Q3) || ((TC_PAIR_REGS & 2) && st == ST_I6); }
+constexpr bool tc_step_in_regs(int st) { return st == ST_G2 || (TC_MERGE_G4 && st == ST_G4) || (TC_I9_REGS && st == ST_I9); }
 struct TcChunk { uint32_t src_off, bytes; };
 #define TC_MAX_OPS 96
 #define TC_MAX_CHUNKS 64
@@ -166,9 +138,6 @@ struct TcTables {                        // global memory (context-owned); copie
     alignas(16) float kpt4[TC_MAXV * NKPT * 4];   // keypoints in each source camera frame (per frame), xyz + pad
     alignas(16) float at2[2 * 3 * 12];   // GeoVisFusion attention layer 2 (3 x 10, rows padded to 12), scale 64 then 8: fp32, in registers
     alignas(16) float out2w[8];          // IBRRenderingHead out_layer, last Linear (8 -> 1): fp32, in registers (TC_I9_REGS)
-    alignas(16) float post2w[2 * 64];    // density head, last Linear (64 -> 2): fp32, in registers (TC_PAIR_REGS)
-    alignas(16) float vis2w[32];         // IBRRenderingHead vis2, last Linear (32 -> 1): fp32, in registers (TC_PAIR_REGS)
-    alignas(16) float out1w[16 * 8];     // out_layer, second Linear (16 -> 8), input-major [i][j]: fp32, in registers (TC_I8_REGS)
     uint16_t bias_off[L_COUNT + 1];      // offset of each biased layer's bias in `bias`
     float ani_al_abs;
 };
@@ -200,13 +169,8 @@ constexpr TcSpecC kSpecs[] = {
     {ST_G3, L_GEO8_F0, 3, 16, 64, 0, 32, 0},
     {ST_G4, L_GEO_F1, 4, 0, 0, 0, 64, 0}, {ST_G4, L_GEO8_F1, 3, 48, 64, 0, 16, 0},
     {ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, 64, 0},
-#if TC_PMERGE
-    {ST_M0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_M0, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_M0, L_MLP0, 3, 0, 0, 1, 16, 0},       // PE blocks 0, 1, 5
-    {ST_P0, L_MLP0, 0, 0, 0, 1, 64, 0}, {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P0, L_MLP0, 2, 0, 0, 1, 64, 0},       // PE blocks 2, 3, 4
-#else
     {ST_P0, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P1, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P2, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 64, 0},
     {ST_P3, L_MLP0, 1, 0, 0, 1, 64, 0}, {ST_P4, L_MLP0, 2, 0, 0, 1, 64, 0}, {ST_P5, L_MLP0, TC_PE_SLOT2, 0, 0, 1, 16, 0},
-#endif
     {ST_M1, L_MLP1, 1, 0, 0, 0, 64, 0}, {ST_M1, L_MLP1, 2, 0, 0, 1, 64, 0},
     {ST_M2, L_MLP2, 4, 0, 0, 0, 64, 0}, {ST_M2, L_MLP2, 0, 0, 0, 1, 64, 0}, {ST_M2, L_MLP2, 3, 48, 0, 1, 16, 0},
     {ST_M3, L_MLP3, 1, 0, 0, 0, 64, 0}, {ST_M3, L_MLP3, 2, 0, 0, 1, 64, 0},
@@ -364,14 +328,9 @@ static void tc_build_script(std::vector<std::vector<TcOpSpec>>& st) {
     add(ST_G4, L_GEO8_F1, 3, 48, 64, 0, iota_map(0, 8, 16));
     // ---- MLPUNet layers1 (src/utils.py:822-852); layer 0 input = [PE 294 | out64], PE in per-keypoint groups of 8
     add(ST_M0, L_MLP0, TC_M0_SLOT, 0, 0, 0, iota_map(294, 64));
-    for (int q = 0; q < 6; ++q) {
-#if TC_PMERGE
-        const int order[6] = {0, 1, 5, 2, 3, 4}, slot_of[6] = {1, 2, 0, 1, 2, 3};      // PE block -> operand slot; blocks 0, 1, 5 ride in step M0
-        const int s = order[q], step = q < 3 ? ST_M0 : ST_P0, slot = slot_of[s];
-#else
+    for (int s = 0; s < 6; ++s) {
         const int pslot[3] = {1, 2, TC_PE_SLOT2};
-        const int s = q, step = ST_P0 + s, slot = pslot[s % 3];
-#endif
+        const int step = ST_P0 + s, slot = pslot[s % 3];
         std::vector<int> m;
         for (int kl = 0; kl < (s < 5 ? 8 : 2); ++kl)
             for (int f = 0; f < 8; ++f) m.push_back(f < 7 ? f * NKPT + (8 * s + kl) : -1);
@@ -554,10 +513,6 @@ static void tc_build(const vanerf_linear* const* src_in, float ani_al, TcTables&
     }
     T.ani_al_abs = fabsf(ani_al);
     for (int i = 0; i < 8; ++i) T.out2w[i] = src[L_OUT2]->w[i];
-    for (int i = 0; i < 128; ++i) T.post2w[i] = src[L_POST2]->w[i];
-    for (int i = 0; i < 32; ++i) T.vis2w[i] = src[L_VIS2_1]->w[i];
-    for (int i = 0; i < 16; ++i)
-        for (int j = 0; j < 8; ++j) T.out1w[i * 8 + j] = src[L_OUT1]->w[(size_t)j * 16 + i];
     for (int sc = 0; sc < 2; ++sc) {
         const vanerf_linear& L = *src[sc ? L_GEO8_AT1 : L_GEO_AT1];
         for (int j = 0; j < 3; ++j)
@@ -718,7 +673,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
 // Whole warp, converged; `lead` = the elected lane that executes the MMAs and commits.
 template <int ST, int I, bool SPLIT>
 __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint32_t slot_i, uint64_t bd_slot_lo, uint32_t slot_lo, TcShared* sh,
-                                            uint64_t ad_base, uint64_t bd_base, uint32_t tmem, bool lead, int tg) {
+                                            uint64_t ad_base, uint64_t bd_base, uint32_t tmem, bool lead) {
     constexpr TcStep S = kProg.steps[ST];
     constexpr TcOp op = kProg.ops[S.op0 + I];
     constexpr bool first_in_chunk = I == 0 || kProg.ops[S.op0 + (I > 0 ? I - 1 : 0)].last_in_chunk != 0;
@@ -758,10 +713,8 @@ __device__ __forceinline__ void tc_issue_op(uint32_t cc, uint64_t bd_slot, uint3
             tc::umma_commit(&sh->wempty[slot_i]);
             if (SPLIT) tc::umma_commit(&sh->wempty[slot_lo]);
         }
-        constexpr int pf = tc_op_pfree(ST, I);
-        if (pf) tc::umma_commit(&sh->pfree[tg][pf > 0 ? pf - 1 : 0]);
     }
-    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1, SPLIT>(cc, bd_slot, slot_i, bd_slot_lo, slot_lo, sh, ad_base, bd_base, tmem, lead, tg);
+    if constexpr (I + 1 < S.nops) tc_issue_op<ST, I + 1, SPLIT>(cc, bd_slot, slot_i, bd_slot_lo, slot_lo, sh, ad_base, bd_base, tmem, lead);
 }
 // Waits for every weight chunk of step ST (TC_PREWAIT): done BEFORE the wait for the step's operands, because the weights
 // are streamed a step ahead and have normally landed long before the tile's epilogue publishes; the ~100-cycle
@@ -803,7 +756,7 @@ __device__ __forceinline__ void tc_issuer_step(uint32_t& n, uint32_t cc_base, Tc
     // kernel is draining and results are discarded): otherwise the compiler computes the descriptors of all 140-odd
     // MMAs ahead of the waits and spills them to local memory.
     const uint32_t never = ok ? 0u : 16u;
-    tc_issue_op<ST, 0, SPLIT>(cc_base + cc_off, 0, 0, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead, tg);
+    tc_issue_op<ST, 0, SPLIT>(cc_base + cc_off, 0, 0, 0, 0, sh, tc_desc(act_u32 + never), tc_desc(ring_u32 + never), tmem, lead);
     if (lead) {
         if (COMMIT == 0) tc::umma_commit(&sh->acc_bar[tg]);
         else if (COMMIT > 0) tc::umma_commit(&sh->pfree[tg][COMMIT > 0 ? COMMIT - 1 : 0]);
@@ -946,17 +899,6 @@ struct TcTile {
         TC_PROF(4000 + st);              // accumulator complete
     }
     __device__ __forceinline__ void step(int st) { issue(st, 0); wait_acc(st); }
-    // The two threads of a row (warps w and w + 4 of the tile group: same TMEM lanes) swap up to 8 fp32 values: each stores its own
-    // into TMEM columns only it has read (`col_mine`), the two warps meet at their named barrier (ids 3..10), each loads the other's.
-    // Every use is followed by a step publish of both warps before the columns are written again, so one scratch area suffices.
-    __device__ __forceinline__ void pair_exchange8(int col_mine, int col_theirs, const float (&mine)[8], float (&theirs)[8]) const {
-        st8(col_mine, mine);
-        tc::tmem_st_wait();
-        tc::tcgen05_fence_before();
-        tc::named_bar_sync(3 + 4 * tg + (int)((threadIdx.x >> 5) & 3), 64);
-        tc::tcgen05_fence_after();
-        ld8(col_theirs, theirs);
-    }
     // multiply the 8 values of a chunk by per-element gates (fp32 product, one rounding back to bf16 [hi + lo])
     template <bool SPLIT>
     __device__ __forceinline__ void gate_chunk(int s, int chunk, const float (&g)[8]) const {
@@ -1170,31 +1112,17 @@ __device__ __noinline__ void tc_issuer_warp(int tg_in, TcShared* sh, int V, int 
 #if !TC_MERGE_G4
             ISTEP(ST_G4, 0);
 #endif
-#if TC_PMERGE
-            ISTEP(ST_M0, -1); ISTEP(ST_P0, 0);
-#else
             ISTEP(ST_M0, -1); ISTEP(ST_P0, 1); ISTEP(ST_P1, 2); ISTEP(ST_P2, 3); ISTEP(ST_P3, 1); ISTEP(ST_P4, 2); ISTEP(ST_P5, 0);
-#endif
             ISTEP(ST_M1, 0); ISTEP(ST_M2, 0); ISTEP(ST_M3, 0);
         }
-        ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0);
-#if !(TC_PAIR_REGS & 1)
-        ISTEP(ST_Q3, 0);
-#endif
+        ISTEP(ST_Q1, 0); ISTEP(ST_Q2, 0); ISTEP(ST_Q3, 0);
         cc += cc_q;
 #pragma unroll 1
         for (int v = 0; v < V; ++v, cc += cc_t) { ISTEP(ST_T1, 0); ISTEP(ST_T2, 0); ISTEP(ST_T3, 0); ISTEP(ST_T4, 0); }
         // the rendering head runs once per tile for all views
-        ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0);
-#if !(TC_PAIR_REGS & 2)
-        ISTEP(ST_I6, 0);
-#endif
-        ISTEP(ST_I7, 0);
-#if !TC_I8_REGS
-        ISTEP(ST_I8, 0);
+        ISTEP(ST_I1, 0); ISTEP(ST_I2, 0); ISTEP(ST_I3, 0); ISTEP(ST_I4, 0); ISTEP(ST_I5, 0); ISTEP(ST_I6, 0); ISTEP(ST_I7, 0); ISTEP(ST_I8, 0);
 #if !TC_I9_REGS
         ISTEP(ST_I9, 0);
-#endif
 #endif
         cc += cc_i;
     }
@@ -1213,10 +1141,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
     unsigned char* smem = tc_smem_raw;
     TcShared* sh = reinterpret_cast<TcShared*>(smem + TC_OFF_CTRL);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-#if TC_CODE_PAD
-    // developer experiment: shifts every later instruction by TC_CODE_PAD x 16 bytes (code-placement sensitivity of the kernel)
-    tc_code_pad<TC_CODE_PAD>();
-#endif
     const int V = A.V;
     const int n_tiles = (A.n_chunk + TC_ROWS - 1) / TC_ROWS;
     constexpr int TPC = SPLIT ? 1 : TC_TILES;                  // tiles in flight per CTA
@@ -1268,15 +1192,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #endif
         const int row = t.row, h = t.half, tg = t.tg;
         const bool leader = tid == tg * TC_EPI_THREADS;          // issues this tile's record loads
-#if TC_STAGGER
-        // CTAs start out of phase: all of them run the same program on the same amount of work, so without this they request
-        // their operand images from HBM in the same few hundred cycles, every time (148 x 64 KB bursts at the full HBM rate).
-        if (gridDim.x > TC_STAGGER_GROUPS) {
-            const long long t_go = clock64() + (long long)(blockIdx.x % TC_STAGGER_GROUPS) * TC_STAGGER;
-            while (clock64() < t_go) __nanosleep(200);
-        }
-#endif
-        bool prefetched = false;                                 // leader: the next tile's first images are already on their way
 #pragma unroll 1
         for (int pair = blockIdx.x; pair < (SPLIT && tg != 0 ? 0 : n_pairs); pair += gridDim.x) {
             // an odd tile count leaves the last pair's second group without a tile: it re-runs the last tile (the ring
@@ -1286,9 +1201,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             const int isamp = tile_raw < n_tiles ? tile * TC_ROWS + row : A.n_chunk;
             const unsigned char* aux_row = A.aux + ((size_t)tile * TC_ROWS + row) * V * AUXB;
             float wsum = 0.0f;
-            // Operand images of (tile, view) -> slots 0..3 / texture image -> slot 1, requested by the group's leader as soon as
-            // the last MMA that reads the target slots has completed (TC_REC_EARLY: one step before they are needed, so that the
-            // HBM latency of the images hides behind the pooling sums / the steps in between; 0 = at the point of use).
+            // Operand images of (tile, view) -> slots 0..3 / texture image -> slot 1, requested by the group's leader at the point of use,
+            // when every MMA that reads the target slots has completed.  (Requesting them a step early does not pay: section 9 of DESIGN.md.)
             auto load_geo = [&](int tl, int v) {
                 if (TC_ABLATE & 128) return;
                 const unsigned char* rimg = A.rec + ((size_t)tl * V + v) * (NIMG * TC_SLOT);
@@ -1310,10 +1224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
                 // all MMAs that read slots 0..3 have completed (last wait_acc)
-                if (leader) {
-                    if (v == 0 ? !prefetched : !(TC_REC_EARLY & 1)) load_geo(tile, v);
-                    prefetched = false;
-                }
+                if (leader) load_geo(tile, v);
                 const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
                 const float pw = reinterpret_cast<const float*>(aux_row + v * AUXB)[7];
                 TC_PROF(5000 + v);
@@ -1367,14 +1278,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 // PE block s (keypoints 8 s .. 8 s + 7; block 5: two keypoints) -> operand slot `pslot`, this thread's keypoints 8 s + 2 j + h
                 auto gen_pe = [&](int s, int pslot) {
                     const int nk = s < 5 ? 4 : 1;
-#if TC_PE_UNROLL
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j >= nk) break;
-#else
 #pragma unroll 1
                     for (int j = 0; j < nk; ++j) {
-#endif
                         const int kp = 8 * s + 2 * j + h;
                         const float4 kc = reinterpret_cast<const float4*>(t.tb->kpt4)[v * NKPT + kp];
                         const float dx = a0.x - kc.x, dy = a0.y - kc.y, dz = a0.z - kc.z;
@@ -1393,23 +1298,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                                                                     tc_pack_scaled(c2, s4, w), tc::pack_bf16(c4 * w, 0.0f)));
                     }
                 };
-#if TC_PMERGE
-                // two publishes: [out64 (slot 4) | blocks 0, 1 (slots 1, 2) | block 5 (slot 3 cols 0..15)], then [blocks 2, 3, 4 (slots 0, 1, 2)];
-                // the issuer commits the ring-slot barriers 0 / 1 right behind the MMAs of blocks 0 / 1, so blocks 3 / 4 are generated
-                // while the rest of the first step is still running
-                gen_pe(0, 1);
-                gen_pe(1, 2);
-                gen_pe(5, 3);
-                t.issue(ST_M0, -1);
-                gen_pe(2, 0);
-#pragma unroll 1
-                for (int ps = 0; ps < 2; ++ps) {
-                    tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 500 + ps);
-                    t.pfree_bits ^= 1u << ps;
-                    gen_pe(3 + ps, 1 + ps);
-                }
-                t.step(ST_P0);
-#else
                 // seven publishes: out64, then the six blocks through a 3-slot ring
                 t.issue(ST_M0, -1);
 #pragma unroll 1
@@ -1431,7 +1319,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                     tc_wait(&sh->pfree[tg][ps], (t.pfree_bits >> ps) & 1u, sh->abort_flag, 510 + ps);
                     t.pfree_bits ^= 1u << ps;
                 }
-#endif
 #if TC_ROLL_MLP
                 // h0 -> slots 1, 2; h1 -> slots 4, 0; h2 -> slots 1, 2: one copy of the 64-column Softplus epilogue
 #pragma unroll 1
@@ -1447,7 +1334,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 EPI(TA_SOFTPLUS, 64 * h, 4, BIASP(L_MLP2) + 64 * h, 1 + h, 0);        // h2 -> slots 1, 2
                 t.step(ST_M3);
 #endif
-                if ((TC_REC_EARLY & 1) && leader && v + 1 < V) load_geo(tile, v + 1);      // M3 (the last reader of slots 1, 2) has completed
                 // ---- weighted pooling sums over views in TMEM: S1 += w h3, S2 += w h3^2 (pool_ops, src/utils.py:854-880)
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
@@ -1501,7 +1387,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 t.template put8<SPLIT>(2, (c0 >> 3) + 1, q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15]);
             }
             t.step(ST_Q1);
-            if ((TC_REC_EARLY & 2) && leader) load_tex(0);             // Q1 was the last reader of slot 1
             uint4 lat_a = make_uint4(0, 0, 0, 0), lat_b = make_uint4(0, 0, 0, 0);      // h=0: latent cols 0-15, h=1: cols 16-23
             uint4 lat_al = make_uint4(0, 0, 0, 0), lat_bl = make_uint4(0, 0, 0, 0);    // their lo parts (split path)
             auto split8 = [](const float* x, uint4& hi, uint4& lo) {
@@ -1530,26 +1415,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             t.step(ST_Q2);
             float o0, o1;
-#if TC_PAIR_REGS & 1
-            {   // last Linear of the density head (64 -> 2, src/utils.py:687-719) on the 32 Softplus outputs each thread of the row holds
-                float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, other[8];
-                const float* w0 = t.tb->post2w + 32 * h;
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {
-                    float x[16];
-                    t.ld16(32 * h + 16 * g, x);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float a = tc_act<TA_SOFTPLUS>(x[i] + BIASP(L_POST1)[32 * h + 16 * g + i]);
-                        part[0] = fmaf(w0[16 * g + i], a, part[0]);
-                        part[1] = fmaf(w0[64 + 16 * g + i], a, part[1]);
-                    }
-                }
-                t.pair_exchange8(32 * h, 32 * (1 - h), part, other);
-                o0 = (h ? other[0] + part[0] : part[0] + other[0]) + BIASP(L_POST2)[0];      // same order in both threads
-                o1 = (h ? other[1] + part[1] : part[1] + other[1]) + BIASP(L_POST2)[1];
-            }
-#else
             EPI(TA_SOFTPLUS, 32 * h, 2, BIASP(L_POST1) + 32 * h, 0, 4 * h);
             t.step(ST_Q3);
             {
@@ -1558,11 +1423,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 o0 = x[0] + BIASP(L_POST2)[0];
                 o1 = x[1] + BIASP(L_POST2)[1];
             }
-#endif
             // =========================================================== texture branch per view
 #pragma unroll 1
             for (int v = 0; v < V; ++v) {
-                if (leader && (v == 0 ? !(TC_REC_EARLY & 2) : !(TC_REC_EARLY & 4))) load_tex(v);
+                if (leader) load_tex(v);
                 // tail operand [lat24 | extras 8] in slot 2, ray difference (4) in slot 3 cols 0..15
                 if (h == 0) {
                     const float4 a0 = *reinterpret_cast<const float4*>(aux_row + v * AUXB);
@@ -1638,7 +1502,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 }
                 // ---- T3: fused layer 1 (ReLU)
                 t.step(ST_T3);
-                if ((TC_REC_EARLY & 4) && leader && v + 1 < V) load_tex(v + 1);           // T3 was the last reader of slot 1
                 if (h == 0) EPI(TA_RELU, 0, 3, NOBIAS, 4, 0);
                 else {
                     EPI(TA_RELU, 48, 1, NOBIAS, 4, 6);
@@ -1794,40 +1657,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             }
             tc::tmem_st_wait();
             t.step(ST_I5);
-#if TC_PAIR_REGS & 2
-            float vsum[TC_MAXV];
-            {   // vis2's last Linear (32 -> 1, src/model.py:1582-1586) on the 16 ELU outputs per view each thread of the row holds
-                float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, other[8];
-                TC_VLOOP
-                for (int v = 0; v < TC_MAXV; ++v) {
-                    if (v < V) {
-                        float x[16];
-                        t.ld16(48 * v + 16 * h, x);
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc = fmaf(t.tb->vis2w[16 * h + i], tc_act<TA_ELU>(x[i] + BIASP(L_VIS2_0)[16 * h + i]), acc);
-                        part[0] = v == 0 ? acc : part[0]; part[1] = v == 1 ? acc : part[1]; part[2] = v == 2 ? acc : part[2];
-                    }
-                }
-                t.pair_exchange8(16 * h, 16 * (1 - h), part, other);
-#pragma unroll
-                for (int v = 0; v < TC_MAXV; ++v) vsum[v] = h ? other[v] + part[v] : part[v] + other[v];
-            }
-#else
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)
                 if (v < V) tc_epi_store<TA_ELU, 1, SPLIT>(t, 48 * v + 16 * h, BIASP(L_VIS2_0) + 16 * h, t.slot(2 + v), 4 + 2 * h);
             t.step(ST_I6);
-#endif
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v) {
                 if (v < V) {
                     float vv[8], x[16];
-#if TC_PAIR_REGS & 2
-                    vv[0] = tc_sel3(vsum, v);
-#else
                     t.ld8(48 * v, vv);
-#endif
                     t.ld16(160 + 32 * v + 16 * h, x);
                     const float vis2 = tc_act<TA_SIGMOID>(vv[0] + BIASP(L_VIS2_1)[0]) * maskv;
                     // out_layer input [x 32 | vis | ray_diff 4] -> slot 2+v cols 0..47
@@ -1843,49 +1681,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 }
             }
             t.step(ST_I7);
-#if TC_I8_REGS
-            // out_layer's last two Linears (16 -> 8 -> 1, src/model.py:1588-1593) in fp32 registers: s_v = w2 . ELU(W1 ELU(acc_v + b0) + b1) + b2.
-            // One thread per row takes all views (the softmax below needs the three scores in one thread); two round trips less
-            // per tile and no bf16 rounding behind out_layer's first Linear.
-            if (h == 0) {
-                TC_VLOOP
-                for (int v = 0; v < TC_MAXV; ++v) {
-                    if (v < V) {
-                        float x[16], y[8];
-                        t.ld16(16 * v, x);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) x[i] = tc_act<TA_ELU>(x[i] + BIASP(L_OUT0)[i]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) y[j] = BIASP(L_OUT1)[j];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-#if TC_F32X2
-#pragma unroll
-                            for (int j = 0; j < 8; j += 2) {
-                                const float2 r2 = __ffma2_rn(make_float2(t.tb->out1w[i * 8 + j], t.tb->out1w[i * 8 + j + 1]), make_float2(x[i], x[i]),
-                                                             make_float2(y[j], y[j + 1]));
-                                y[j] = r2.x; y[j + 1] = r2.y;
-                            }
-#else
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) y[j] = fmaf(t.tb->out1w[i * 8 + j], x[i], y[j]);
-#endif
-                        }
-                        float sacc = BIASP(L_OUT2)[0];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) sacc = fmaf(t.tb->out2w[j], tc_act<TA_ELU>(y[j]), sacc);
-                        tc_set3(sv, v, (maskv == 0.0f) ? -1e4f : sacc);
-                    }
-                }
-            }
-#else
             TC_VLOOP
             for (int v = 0; v < TC_MAXV; ++v)            // 16 columns per view: views alternate between the two row partners
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT0), t.slot(2 + v), 6);
             t.step(ST_I8);
-#endif
-#if TC_I8_REGS
-#elif TC_I9_REGS
+#if TC_I9_REGS
             // out_layer's last two layers end here: s_v = w2 . ELU(acc_v + b1) + b2 in fp32 registers (8 values per view)
             if (h == 0) {
                 TC_VLOOP
@@ -1906,11 +1706,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
                 if (v < V && (v & 1) == h) tc_epi_store<TA_ELU, 1, SPLIT>(t, 16 * v, BIASP(L_OUT1), t.slot(2 + v), 0);
             t.step(ST_I9);
 #endif
-            if ((TC_REC_EARLY & 8) && leader) {                 // every MMA of this tile has completed: the next tile's first images
-                const int pair_n = pair + gridDim.x;
-                prefetched = pair_n < n_pairs;
-                if (prefetched) load_geo(min(pair_n * TPC + tg, n_tiles - 1), 0);
-            }
 #if !TC_I9_REGS
             if (h == 0) {
                 TC_VLOOP
@@ -1961,10 +1756,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(TcArgs A) {
             if (leader) sh->stop[tg] = *reinterpret_cast<volatile int*>(sh->abort_flag);
             tc::named_bar_sync(1 + tg, TC_EPI_THREADS);
             if (*reinterpret_cast<volatile int*>(&sh->stop[tg])) break;
-        }
-        if (TC_REC_EARLY && leader && prefetched) {              // left the loop on an abort with images in flight: they must land before the CTA exits
-#pragma unroll 1
-            for (int it = 0; it < TC_WAIT_TRIES && !tc::mbar_try_wait(&sh->rec_bar[tg], t.rec_phase); ++it) {}
         }
     }
     tc_teardown(sh, A.err);
