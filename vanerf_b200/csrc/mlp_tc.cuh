@@ -41,7 +41,9 @@
 #define TC_TILES 2                       // tiles in flight per CTA
 #define TC_EPI_THREADS 256               // threads of one tile group
 #define TC_THREADS (TC_TILES * TC_EPI_THREADS + 128)   // + one warpgroup: weight producer warp, one MMA issuer warp per tile, one parked warp
+#ifndef TC_REGS_EPI
 #define TC_REGS_EPI 112                  // registers of a tile thread after setmaxnreg (kernel is compiled for 96)
+#endif
 #define TC_REGS_PROD 32                  // registers of the producer / issuer warpgroup (gives 64 x 128 back to the pool)
 #define TC_NREADY 4                      // operand-ready barriers per tile: a warp runs at most 3 steps ahead of the slowest (PE ring)
 #define TC_TMEM_COLS 512
