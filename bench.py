@@ -275,7 +275,10 @@ def measure_train(args, steps, warmup, patch=64):
         torch.cuda.synchronize()
 
     res = {}
-    for mode in ("resident", "e2e"):
+    for mode in ("resident", "e2e", "tf32"):
+        # "tf32": the same resident step with the dense layers of the training graph on TF32 tensor cores (opt-in, T.matmul_precision)
+        ctx = T.matmul_precision("tf32" if mode == "tf32" else "fp32")
+        ctx.__enter__()
         for _ in range(warmup):
             step(mode == "e2e")
         sync_all()
@@ -291,6 +294,7 @@ def measure_train(args, steps, warmup, patch=64):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[mode] = (float(t.item()) / steps, path.renderer.launches - l0, float(loss))
+        ctx.__exit__(None, None, None)
     if rank != 0:
         return None
     ms, launches, loss = res["resident"]
@@ -308,6 +312,9 @@ def measure_train(args, steps, warmup, patch=64):
                        "parameters": n_params, "allreduce_bytes": 4 * n_params, "where": "gpu"},
             "e2e": {"value": rays / (ms_e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "loss": loss, "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+            "tf32_variant": {"ms_per_step": res["tf32"][0], "value": rays / (res["tf32"][0] * 1e-3), "unit": "rays/s",
+                             "note": "NOT the headline: dense layers of the training graph on TF32 tensor cores (vanerf_b200.train.matmul_precision('tf32')); "
+                                     "the headline and the gradient-parity tests run exact fp32"},
             "roofline": {"kernel": "dense layers of the unfused training graph (cuBLAS fp32 GEMMs, library)", "bound": "tensor",
                          "achieved": flops / (ms * 1e-3) / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / pk["tf_sust"],
                          "traffic": None, "note": "whole step time; fp32 SGEMM cannot reach the bf16 tensor peak it is divided by"}}

@@ -97,11 +97,38 @@ class CompositeFn(torch.autograd.Function):
         return None, d_rgba, None, None, d_beta
 
 
+TF32 = False        # module switch set by `matmul_precision`: the training graph's GEMMs and convolutions on TF32 tensor cores
+
+
 def fp32_exact():
     """Context for forward AND backward of the training graph: cuDNN / cuBLAS in true fp32 (no TF32), deterministic algorithms.
     The reference's own GPU run takes TF32 for its convolutions; the CPU oracle is the arbiter here.  The
-    backward of a convolution reads these flags when it RUNS, so `loss.backward()` belongs inside the context too."""
-    return torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True, allow_tf32=False)
+    backward of a convolution reads these flags when it RUNS, so `loss.backward()` belongs inside the context too.
+    Inside `matmul_precision("tf32")` the convolutions follow the GEMMs onto the tensor cores."""
+    return torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=not TF32, allow_tf32=TF32)
+
+
+class matmul_precision:
+    """`with matmul_precision("tf32"):` runs the dense layers of the unfused training graph (cuBLAS GEMMs, cuDNN convolutions) on TF32
+    tensor cores (10-bit mantissa operands, fp32 accumulation) for the steps inside it; "fp32" (the default everywhere, and what the
+    gradient-parity tests run) keeps them exact.  An opt-in like the bf16-MLP path of inference: faster, not bit-comparable."""
+
+    def __init__(self, mode: str = "fp32"):
+        if mode not in ("fp32", "tf32"):
+            raise ValueError("matmul_precision: 'fp32' or 'tf32'")
+        self.on = mode == "tf32"
+
+    def __enter__(self):
+        global TF32
+        self.prev = (TF32, torch.backends.cuda.matmul.allow_tf32)
+        TF32 = self.on
+        torch.backends.cuda.matmul.allow_tf32 = self.on
+        return self
+
+    def __exit__(self, *exc):
+        global TF32
+        TF32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
 
 
 # ---------------------------------------------------------------------------------------------------- randomness
@@ -245,6 +272,7 @@ class TrainableRenderPath(torch.nn.Module):
         twin = (nn + NUM_V) % (2 * NUM_V)
         vis = self.vert_vis
         vn, vt = vis[:, nn][..., None], vis[:, twin][..., None]              # (V,N,1)
+        rows = lambda T, idx: torch.index_select(T, 1, idx)                  # T[:, idx]; its backward is one index_add_ (advanced indexing sorts)
         sdf = geo["sdf"][None, :, None].expand(V, -1, -1)
         qv = geo["qvis"].float()[..., None]
         # ---- GeoVisFusion (src/networks.py:75-106)
@@ -252,7 +280,7 @@ class TrainableRenderPath(torch.nn.Module):
         for g, T, at, ff in ((self.g0, T64, "geo_vis_fusion.fconv_at", "geo_vis_fusion.fconv_ated"),
                              (self.g1, T8, "geo_vis_fusion.fconv_at1", "geo_vis_fusion.fconv_ated1")):
             px = FeatSampleFn.apply(r, g, xy)
-            a, b = T[:, nn] * vn, T[:, twin] * vt
+            a, b = rows(T, nn) * vn, rows(T, twin) * vt
             x = torch.cat([px, a, b, sdf, qv, vn, vt], 2)
             att = torch.sigmoid(self._conv1(F.relu(self._conv1(x, at + ".0")), at + ".2"))
             y = torch.cat([px * att[..., 0:1], a * att[..., 1:2], b * att[..., 2:3], sdf, qv, vn, vt], 2)
@@ -275,7 +303,7 @@ class TrainableRenderPath(torch.nn.Module):
         # ---- query_color: TexVisFusion + IBRRenderingHead (src/model.py:904-951, networks.py:268-293, model.py:1600-1636)
         lat24 = self._lin(latent, "ibr_compress_gfeat")[None].expand(V, -1, -1)
         q = torch.cat([FeatSampleFn.apply(r, self.img, xy), FeatSampleFn.apply(r, self.tex, xy)], 2)
-        a, b = Tt[:, nn] * vn, Tt[:, twin] * vt
+        a, b = rows(Tt, nn) * vn, rows(Tt, twin) * vt
         a11, a18, b11, b18 = a[..., :11], a[..., 11:], b[..., :11], b[..., 11:]
         y = torch.cat([q, a11, b11, a18, b18, lat24, qv, vn, vt], 2)
         att = torch.sigmoid(self._conv1(F.relu(self._conv1(y, "tex_vis_fusion.fconv_at.0")), "tex_vis_fusion.fconv_at.2"))
