@@ -28,7 +28,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // One try_wait: suspends the warp in hardware until the phase completes or the suspend-time hint (ns) runs out, so a
 // waiting warp does not burn issue slots polling.
+#ifndef TC_WAIT_HINT_NS
 #define TC_WAIT_HINT_NS 20000u
+#endif
 // A wait gives up after TC_WAIT_TRIES tries: ~21 s when the suspend-time hint is honoured in full, ~0.1 s when every try
 // returns at once (~150 cycles per try); legitimate waits of these kernels are below a millisecond, so neither time slicing,
 // MPS nor a debugger stretching or shortening the tries can trip the bound, and a protocol bug still ends in seconds.
